@@ -1,0 +1,183 @@
+/* smt_b200.h -- C ABI of the B200-native stereo-matching engine (libsmt_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The reference
+ * (Asherchi/Stereo_Match_Traditional) has no FFI of its own; its "API" is a set of classes and free
+ * functions on raw host arrays.  Each entry point below names the reference interface it replaces
+ * (file:line under the reference tree); include/smt_b200.hpp re-creates those classes on top of this
+ * ABI, and INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - Volumes are float32 [rows][cols][D], D innermost: idx = (i*cols + j)*D + d   (AD-Census.h:87).
+ *   - Images are row-major; BGR images are interleaved uint8 [rows][cols][3]      (cross_aggregator.cpp:138).
+ *   - Every function returns smt_status_t; nothing throws or aborts across the ABI.
+ *   - `space` says where ALL pointer arguments of that call live: SMT_HOST (the reference's convention;
+ *     the call copies in, runs on the context's stream, copies out and synchronises) or SMT_DEVICE
+ *     (pointers are CUDA device pointers on the context's device; the call only enqueues work on the
+ *     context's stream -- use smt_sync()).
+ *   - One smt_ctx per (device, stream).  Calls on one context are serialised by the caller; contexts are
+ *     independent (one per GPU for batched frame streams).
+ *   - There is no CPU fallback: without a CUDA device smt_create() fails with SMT_ERR_CUDA.
+ */
+#ifndef SMT_B200_H_
+#define SMT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SMT_API __declspec(dllexport)
+#else
+#define SMT_API __attribute__((visibility("default")))
+#endif
+
+typedef struct smt_ctx smt_ctx;
+
+typedef int32_t smt_status_t;
+enum {
+    SMT_OK = 0,
+    SMT_ERR_INVALID_ARG = 1,  /* null pointer, non-positive size, ...                                   */
+    SMT_ERR_UNSUPPORTED = 2,  /* shape/parameter outside what the reference itself defines (see docs)    */
+    SMT_ERR_OOM = 3,          /* device allocation failed                                                */
+    SMT_ERR_CUDA = 4,         /* CUDA runtime error; smt_last_error_string() has the text                */
+    SMT_ERR_INPUT_RANGE = 5   /* float image is not integer-valued in 0..255 (AD-CensusV1/main.cpp:50-53) */
+};
+
+typedef int32_t smt_memspace_t;
+enum { SMT_HOST = 0, SMT_DEVICE = 1 };
+
+/* Summation order of the float32 aggregation passes. */
+typedef int32_t smt_sum_mode_t;
+enum {
+    SMT_SUM_REFERENCE_ORDER = 0, /* per-cell sequential adds in the reference's tap order: bit-exact          */
+    SMT_SUM_FAST = 1             /* shared-memory line scans, window sums rounded once: <=1e-5 relative    */
+};
+
+/* ------------------------------------------------------------------------------------------------ context */
+SMT_API int32_t smt_abi_version(void);
+/* stream: a cudaStream_t (as void*) to enqueue on, or NULL to let the context create its own. */
+SMT_API smt_status_t smt_create(int32_t device, void* stream, smt_ctx** out);
+SMT_API void smt_destroy(smt_ctx* ctx);
+SMT_API smt_status_t smt_sync(smt_ctx* ctx);
+SMT_API const char* smt_last_error_string(const smt_ctx* ctx);
+SMT_API const char* smt_status_string(smt_status_t st);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+SMT_API uint64_t smt_kernel_launches(const smt_ctx* ctx);
+/* CUDA-event time (ms) accumulated per pipeline stage since the last reset; stage names via smt_stage_name */
+SMT_API int32_t smt_num_stages(void);
+SMT_API const char* smt_stage_name(int32_t stage);
+SMT_API smt_status_t smt_stage_timing_enable(smt_ctx* ctx, int32_t enable);
+SMT_API smt_status_t smt_stage_timing_read(smt_ctx* ctx, double* ms_per_stage, int32_t reset);
+/* free cached device workspace */
+SMT_API smt_status_t smt_trim(smt_ctx* ctx);
+/* plain device memory helpers so a host language needs nothing but this library */
+SMT_API smt_status_t smt_device_alloc(smt_ctx* ctx, size_t bytes, void** out);
+SMT_API smt_status_t smt_device_free(smt_ctx* ctx, void* p);
+SMT_API smt_status_t smt_memcpy_h2d(smt_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+SMT_API smt_status_t smt_memcpy_d2h(smt_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------ AD-Census cost
+ * Replaces AD_Census::{Initialize, ComputeAD[Right], ComputeCensus9x7[Right], ComputeADcensus[Right]}
+ * (AD-CensusV1/AD-Census.h:322, :75/:103, :142/:207, :271/:296).
+ * left/right: float32 [rows][cols] holding integer grey values 0..255 (main.cpp:50-53).
+ * view 0 = left cost (match at j-d), 1 = right cost (match at j+d).
+ * cost (required), ad, census (optional, may be NULL): float32 [rows][cols][D].
+ */
+SMT_API smt_status_t smt_adcensus_cost(smt_ctx* ctx, const float* left, const float* right, int32_t rows,
+                                       int32_t cols, int32_t D, float sigmaC, float sigmaS, int32_t view,
+                                       float* cost, float* ad, float* census, smt_memspace_t space);
+
+/* The packed 63-bit 9x7 census string of every pixel of one image, in the reference's bit order: the tap
+ * (r,c), r=-4..4 outer, c=-3..3 inner, is shifted in MSB-first, so tap (-4,-3) is bit 62 and (4,3) bit 0;
+ * out-of-image taps contribute 0 (AD-Census.h:167-191).  img: float32 [rows][cols]; out: uint64 [rows][cols]. */
+SMT_API smt_status_t smt_census9x7_u64(smt_ctx* ctx, const float* img, int32_t rows, int32_t cols, uint64_t* out,
+                                       smt_memspace_t space);
+
+/* First-minimum winner-take-all over d, disparity stored as float.  Replaces AD_Census::WTA (AD-Census.h:346),
+ * CrossArmAggregation::WTA (CrossArm.cpp:33), ScanlineOptimizer::WTA (ScanlineOptimizer.h:40) and
+ * ComputeDispOringin (CBLSM/CBLSM.h:383). */
+SMT_API smt_status_t smt_wta_first_min(smt_ctx* ctx, const float* vol, int32_t rows, int32_t cols, int32_t D,
+                                       float* disp, smt_memspace_t space);
+
+/* ------------------------------------------------------------------------------------------------ CrossAggregator
+ * Replaces CrossAggregator::{Initialize, SetData, SetParams, BuildArms, ComputeSupPixelCount, Aggregate}
+ * (CBLSM/cross_aggregator.cpp:19-118, :135-394).
+ * bgr: uint8 [rows][cols][3] (arms come from this image only, :138,:206).
+ * arms_out (optional): uint8 [rows][cols][4] = {left,right,top,bottom} (cross_aggregator.h:17-20);
+ * sup_hfirst / sup_vfirst (optional): uint16 [rows][cols] (vec_sup_count_[0], [1]).
+ */
+SMT_API smt_status_t smt_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int32_t cols, int32_t L1,
+                                    int32_t L2, int32_t t1, int32_t t2, uint8_t* arms_out, uint16_t* sup_hfirst,
+                                    uint16_t* sup_vfirst, smt_memspace_t space);
+SMT_API smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const float* cost_init, int32_t rows,
+                                         int32_t cols, int32_t D, int32_t L1, int32_t L2, int32_t t1, int32_t t2,
+                                         int32_t iters, smt_sum_mode_t mode, float* cost_out, uint8_t* arms_out,
+                                         uint16_t* sup_hfirst, uint16_t* sup_vfirst, smt_memspace_t space);
+
+/* ------------------------------------------------------------------------------------------------ ScanlineOptimizer
+ * Replaces ScanlineOptimizer::{Initialize, ScanLine, ScanLineLeftRight, ScanLineUpDown, WTA}
+ * (AD-CensusV1/ScanlineOptimizer.h:66, :104, :130, :194, :40) including the up/down quirks (:221,:232,:238).
+ * cost: float32 [rows][cols][D]; gray: float32 [rows][cols]; p1, p2 are ints as in the reference (:66).
+ * Optional outputs (NULL to skip): the four path volumes, their sum (_ProcessedVolume) and the WTA disparity.
+ */
+SMT_API smt_status_t smt_scanline(smt_ctx* ctx, const float* cost, const float* gray, int32_t rows, int32_t cols,
+                                  int32_t D, int32_t p1, int32_t p2, float* left, float* right, float* up,
+                                  float* down, float* sum, float* disp, smt_memspace_t space);
+
+/* ------------------------------------------------------------------------------------------------ post-processing
+ * smt_lrcheck replaces LeftRightConsistency (AD-CensusV1/PostProcessing.h:72): disp_left is modified in place
+ * (+inf at invalidated pixels); occ / mis receive (row, col) int32 pairs in the reference's row-major emission
+ * order (capacity rows*cols pairs each, may be NULL), n_occ / n_mis their counts (host pointers in both spaces).
+ * smt_lrcheck_and replaces LeftAndRightConsistency (:10): writes 0 / d into `last`, `>=` float gate.
+ */
+SMT_API smt_status_t smt_lrcheck(smt_ctx* ctx, float* disp_left, const float* disp_right, int32_t cols,
+                                 int32_t rows, int32_t gate, int32_t* occ, int32_t* n_occ, int32_t* mis,
+                                 int32_t* n_mis, smt_memspace_t space);
+SMT_API smt_status_t smt_lrcheck_and(smt_ctx* ctx, const float* disp_left, const float* disp_right, float* last,
+                                     int32_t cols, int32_t rows, float gate, int32_t* occ, int32_t* n_occ,
+                                     int32_t* mis, int32_t* n_mis, smt_memspace_t space);
+/* Replaces RemoveSpeckles (PostProcessing.h:250).  invalid_val is the reference's *int* parameter; the shipped
+ * call passes +inf, which g++ folds to 2147483647 (main.cpp:93) -- pass that to reproduce it. */
+SMT_API smt_status_t smt_remove_speckles(smt_ctx* ctx, float* disp, int32_t cols, int32_t rows, int32_t diff,
+                                         uint32_t min_area, int32_t invalid_val, smt_memspace_t space);
+/* Replaces MedianFilter (PostProcessing.h:314): in-bounds taps only, element sorted[n/2]; odd wnd_size <= 9. */
+SMT_API smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32_t cols, int32_t rows,
+                                int32_t wnd_size, smt_memspace_t space);
+
+/* ------------------------------------------------------------------------------------------------ full pipeline
+ * P_full: the composition of the reference entry points above with the reference's own
+ * default parameters (main.cpp:24-30, adcensus_types.h:69-70).
+ */
+typedef struct smt_adcensus_params {
+    int32_t rows, cols, D;
+    float sigmaC, sigmaS;          /* main.cpp:25-26,58 : 10, 30          */
+    int32_t L1, L2, t1, t2;        /* adcensus_types.h:69-70 : 34,17,20,6 */
+    int32_t agg_iters;             /* CBLSM.cpp:141 : 4                   */
+    int32_t p1, p2;                /* main.cpp:28-29 : 10, 150            */
+    int32_t gate;                  /* main.cpp:30 : 2                     */
+    int32_t speckle_diff;          /* main.cpp:93 : 1                     */
+    uint32_t speckle_min_area;     /* main.cpp:93 : 30                    */
+    int32_t speckle_invalid;       /* main.cpp:93 : +inf -> 2147483647    */
+    int32_t median_size;           /* main.cpp:94 : 3                     */
+    smt_sum_mode_t sum_mode;
+} smt_adcensus_params;
+SMT_API void smt_adcensus_default_params(smt_adcensus_params* p, int32_t rows, int32_t cols, int32_t D);
+/* bgr_*: uint8 [rows][cols][3]; gray_*: uint8 [rows][cols].
+ * Outputs (all optional except disp_out), float32 [rows][cols]:
+ *   disp_out        after LR check + speckle removal + median
+ *   disp_left_raw   ScanlineOptimizer::WTA of the left view
+ *   disp_right_raw  first-min WTA of the aggregated right volume
+ *   disp_lrc        left disparity after LeftRightConsistency (+inf = invalidated)
+ */
+SMT_API smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcensus_params* p, const uint8_t* bgr_left,
+                                                const uint8_t* bgr_right, const uint8_t* gray_left,
+                                                const uint8_t* gray_right, float* disp_out, float* disp_left_raw,
+                                                float* disp_right_raw, float* disp_lrc, smt_memspace_t space);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMT_B200_H_ */

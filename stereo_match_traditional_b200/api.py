@@ -1,0 +1,448 @@
+"""Host-side mirror of the reference's per-method entry points, on top of the C ABI.
+
+``Engine`` wraps one ``smt_ctx`` (one per GPU / stream) and exposes every C-ABI call with numpy arrays (host
+memspace: the reference's own convention -- caller-owned host arrays) or torch CUDA tensors (device memspace:
+nothing crosses PCIe).  The classes and functions below it keep the reference's names, argument order and
+meaning so call sites and tests read like the reference's:
+
+    AD_Census            AD-CensusV1/AD-Census.h:9-43
+    CrossAggregator      CBLSM/cross_aggregator.h:27-113
+    ScanlineOptimizer    AD-CensusV1/ScanlineOptimizer.h:8-34
+    LeftRightConsistency, LeftAndRightConsistency, RemoveSpeckles, MedianFilter   AD-CensusV1/PostProcessing.h
+
+PyTorch is used only for device memory and streams; all compute is in libsmt_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SMT_DEVICE, SMT_HOST, SUM_FAST, SUM_REFERENCE_ORDER, AdCensusParams
+
+__all__ = [
+    "Engine", "SmtError", "default_engine", "AD_Census", "CrossAggregator", "ScanlineOptimizer",
+    "LeftRightConsistency", "LeftAndRightConsistency", "RemoveSpeckles", "MedianFilter", "Invalid_Float",
+    "SUM_FAST", "SUM_REFERENCE_ORDER",
+]
+
+Invalid_Float = float("inf")  # PostProcessing.h:7
+INVALID_INT_FROM_INF = 2147483647  # what `const int& invalid_val = Invalid_Float` becomes under g++ (main.cpp:93)
+
+
+class SmtError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"smt status {status}: {text}")
+        self.status = status
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Args:
+    """Collects arguments of one call, decides the memspace, keeps temporaries alive."""
+
+    def __init__(self, engine: "Engine", *inputs):
+        self.engine = engine
+        self.device = any(_is_torch(a) and a.is_cuda for a in inputs if a is not None)
+        self.keep = []
+
+    @property
+    def space(self) -> int:
+        return SMT_DEVICE if self.device else SMT_HOST
+
+    def inp(self, a, dtype, shape=None):
+        if a is None:
+            return None
+        if self.device:
+            import torch
+
+            tdt = getattr(torch, np.dtype(dtype).name)
+            if not _is_torch(a):
+                a = torch.as_tensor(np.ascontiguousarray(a, dtype=dtype), device=f"cuda:{self.engine.device}")
+            if a.dtype != tdt:
+                raise TypeError(f"expected {tdt}, got {a.dtype}")
+            a = a.contiguous()
+            self.keep.append(a)
+            if shape is not None and tuple(a.shape) != tuple(shape):
+                raise ValueError(f"expected shape {shape}, got {tuple(a.shape)}")
+            return C.c_void_p(a.data_ptr())
+        a = np.ascontiguousarray(a, dtype=dtype)
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"expected shape {shape}, got {a.shape}")
+        self.keep.append(a)
+        return C.c_void_p(a.ctypes.data)
+
+    def out(self, shape, dtype, want=True, init=None):
+        """Allocate an output (numpy or torch).  Returns (array, pointer)."""
+        if not want:
+            return None, None
+        if self.device:
+            import torch
+
+            tdt = {np.uint64: torch.int64}.get(dtype, None) or getattr(torch, np.dtype(dtype).name)
+            t = torch.empty(tuple(shape), dtype=tdt, device=f"cuda:{self.engine.device}")
+            if init is not None:
+                t.copy_(init if _is_torch(init) else torch.as_tensor(np.asarray(init)))
+            self.keep.append(t)
+            return t, C.c_void_p(t.data_ptr())
+        a = np.empty(tuple(shape), dtype=dtype)
+        if init is not None:
+            a[...] = init
+        self.keep.append(a)
+        return a, C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One ``smt_ctx``: a device, a stream, a cached device workspace."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        st = self.lib.smt_create(self.device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if st != 0:
+            raise SmtError(st, "smt_create failed (no CUDA device? this library has no CPU fallback): "
+                           + self.lib.smt_status_string(st).decode())
+        self.h = h
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, st: int):
+        if st != 0:
+            raise SmtError(st, self.lib.smt_last_error_string(self.h).decode() or self.lib.smt_status_string(st).decode())
+
+    def sync(self):
+        self._ck(self.lib.smt_sync(self.h))
+
+    def trim(self):
+        self._ck(self.lib.smt_trim(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.smt_kernel_launches(self.h))
+
+    def stage_timing(self, enable: bool):
+        self._ck(self.lib.smt_stage_timing_enable(self.h, int(enable)))
+
+    def read_stage_timing(self, reset: bool = True) -> dict:
+        n = self.lib.smt_num_stages()
+        buf = (C.c_double * n)()
+        self._ck(self.lib.smt_stage_timing_read(self.h, buf, int(reset)))
+        return {self.lib.smt_stage_name(k).decode(): float(buf[k]) for k in range(n)}
+
+    # ------------------------------------------------------------------ AD-Census
+    def adcensus_cost(self, left, right, D: int, sigmaC: float = 10.0, sigmaS: float = 30.0, view: int = 0,
+                      want_ad: bool = False, want_census: bool = False):
+        """AD_Census::ComputeADcensus (view 0) / ComputeADcensusRight (view 1).  Returns dict(cost[, ad, census])."""
+        a = _Args(self, left, right)
+        H, W = left.shape
+        pl = a.inp(left, np.float32, (H, W))
+        pr = a.inp(right, np.float32, (H, W))
+        cost, pc = a.out((H, W, D), np.float32)
+        ad, pa = a.out((H, W, D), np.float32, want_ad)
+        cen, pn = a.out((H, W, D), np.float32, want_census)
+        self._ck(self.lib.smt_adcensus_cost(self.h, pl, pr, H, W, D, sigmaC, sigmaS, view, pc, pa, pn, a.space))
+        out = {"cost": cost}
+        if want_ad:
+            out["ad"] = ad
+        if want_census:
+            out["census"] = cen
+        return out
+
+    def census9x7(self, img):
+        a = _Args(self, img)
+        H, W = img.shape
+        pi = a.inp(img, np.float32, (H, W))
+        out, po = a.out((H, W), np.uint64)
+        self._ck(self.lib.smt_census9x7_u64(self.h, pi, H, W, po, a.space))
+        return out
+
+    def wta(self, vol):
+        a = _Args(self, vol)
+        H, W, D = vol.shape
+        pv = a.inp(vol, np.float32)
+        disp, pd = a.out((H, W), np.float32)
+        self._ck(self.lib.smt_wta_first_min(self.h, pv, H, W, D, pd, a.space))
+        return disp
+
+    # ------------------------------------------------------------------ CrossAggregator
+    def cross_arms(self, bgr, L1=34, L2=17, t1=20, t2=6):
+        a = _Args(self, bgr)
+        H, W = bgr.shape[:2]
+        pb = a.inp(bgr, np.uint8, (H, W, 3))
+        arms, pa = a.out((H, W, 4), np.uint8)
+        s0, p0 = a.out((H, W), np.uint16)
+        s1, p1 = a.out((H, W), np.uint16)
+        self._ck(self.lib.smt_cross_arms(self.h, pb, H, W, L1, L2, t1, t2, pa, p0, p1, a.space))
+        return {"arms": arms, "sup0": s0, "sup1": s1}
+
+    def aggregate_cross(self, bgr, cost, L1=34, L2=17, t1=20, t2=6, iters=4, mode=SUM_REFERENCE_ORDER,
+                        want_arms: bool = False):
+        a = _Args(self, bgr, cost)
+        H, W, D = cost.shape
+        pb = a.inp(bgr, np.uint8, (H, W, 3))
+        pc = a.inp(cost, np.float32)
+        out, po = a.out((H, W, D), np.float32)
+        arms, pa = a.out((H, W, 4), np.uint8, want_arms)
+        s0, p0 = a.out((H, W), np.uint16, want_arms)
+        s1, p1 = a.out((H, W), np.uint16, want_arms)
+        self._ck(self.lib.smt_aggregate_cross(self.h, pb, pc, H, W, D, L1, L2, t1, t2, iters, mode, po, pa, p0, p1, a.space))
+        res = {"cost": out}
+        if want_arms:
+            res.update(arms=arms, sup0=s0, sup1=s1)
+        return res
+
+    # ------------------------------------------------------------------ ScanlineOptimizer
+    def scanline(self, cost, gray, p1=10, p2=150, want: Sequence[str] = ("sum", "disp")):
+        a = _Args(self, cost, gray)
+        H, W, D = cost.shape
+        pc = a.inp(cost, np.float32)
+        pg = a.inp(gray, np.float32, (H, W))
+        names = ["left", "right", "up", "down", "sum", "disp"]
+        outs, ptrs = {}, []
+        for n in names:
+            arr, p = a.out((H, W) if n == "disp" else (H, W, D), np.float32, n in want)
+            if n in want:
+                outs[n] = arr
+            ptrs.append(p)
+        self._ck(self.lib.smt_scanline(self.h, pc, pg, H, W, D, int(p1), int(p2), *ptrs, a.space))
+        return outs
+
+    # ------------------------------------------------------------------ post-processing
+    def lrcheck(self, dispL, dispR, gate=2, want_lists: bool = True):
+        """LeftRightConsistency.  Returns (dispL_out, occlusions[n,2], mismatches[m,2])."""
+        a = _Args(self, dispL, dispR)
+        H, W = dispL.shape
+        d, pd = a.out((H, W), np.float32, init=dispL)
+        pr = a.inp(dispR, np.float32, (H, W))
+        occ, po = a.out((H * W, 2), np.int32, want_lists)
+        mis, pm = a.out((H * W, 2), np.int32, want_lists)
+        no, nm = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.smt_lrcheck(self.h, pd, pr, W, H, int(gate), po, C.byref(no), pm, C.byref(nm), a.space))
+        if not want_lists:
+            return d, no.value, nm.value
+        return d, occ[: no.value], mis[: nm.value]
+
+    def lrcheck_and(self, dispL, dispR, gate=2.0, want_lists: bool = True):
+        """LeftAndRightConsistency.  Returns (lastDisp, occlusions, mismatches)."""
+        a = _Args(self, dispL, dispR)
+        H, W = dispL.shape
+        pl = a.inp(dispL, np.float32, (H, W))
+        pr = a.inp(dispR, np.float32, (H, W))
+        last, plast = a.out((H, W), np.float32)
+        occ, po = a.out((H * W, 2), np.int32, want_lists)
+        mis, pm = a.out((H * W, 2), np.int32, want_lists)
+        no, nm = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.smt_lrcheck_and(self.h, pl, pr, plast, W, H, float(gate), po, C.byref(no), pm, C.byref(nm), a.space))
+        if not want_lists:
+            return last, no.value, nm.value
+        return last, occ[: no.value], mis[: nm.value]
+
+    def remove_speckles(self, disp, diff=1, min_area=30, invalid=INVALID_INT_FROM_INF):
+        a = _Args(self, disp)
+        H, W = disp.shape
+        d, pd = a.out((H, W), np.float32, init=disp)
+        self._ck(self.lib.smt_remove_speckles(self.h, pd, W, H, int(diff), int(min_area), int(invalid), a.space))
+        return d
+
+    def median(self, disp, k=3):
+        a = _Args(self, disp)
+        H, W = disp.shape
+        pi = a.inp(disp, np.float32, (H, W))
+        out, po = a.out((H, W), np.float32)
+        self._ck(self.lib.smt_median(self.h, pi, po, W, H, int(k), a.space))
+        return out
+
+    # ------------------------------------------------------------------ full pipeline
+    def default_params(self, H, W, D) -> AdCensusParams:
+        p = AdCensusParams()
+        self.lib.smt_adcensus_default_params(C.byref(p), H, W, D)
+        return p
+
+    def pipeline(self, bgr_left, bgr_right, D, gray_left=None, gray_right=None, params: Optional[AdCensusParams] = None,
+                 want: Sequence[str] = ("disp",), **overrides):
+        """P_full.  ``want`` from {"disp", "left_raw", "right_raw", "lrc"}; keyword overrides set params fields."""
+        a = _Args(self, bgr_left, bgr_right)
+        H, W = bgr_left.shape[:2]
+        p = params or self.default_params(H, W, D)
+        for k, v in overrides.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown pipeline parameter {k!r}")
+            setattr(p, k, v)
+        pbl = a.inp(bgr_left, np.uint8, (H, W, 3))
+        pbr = a.inp(bgr_right, np.uint8, (H, W, 3))
+        pgl = a.inp(gray_left, np.uint8, (H, W))
+        pgr = a.inp(gray_right, np.uint8, (H, W))
+        disp, pd = a.out((H, W), np.float32)
+        lraw, p1 = a.out((H, W), np.float32, "left_raw" in want)
+        rraw, p2 = a.out((H, W), np.float32, "right_raw" in want)
+        lrc, p3 = a.out((H, W), np.float32, "lrc" in want)
+        self._ck(self.lib.smt_pipeline_adcensus_full(self.h, C.byref(p), pbl, pbr, pgl, pgr, pd, p1, p2, p3, a.space))
+        out = {"disp": disp}
+        for n, v in (("left_raw", lraw), ("right_raw", rraw), ("lrc", lrc)):
+            if n in want:
+                out[n] = v
+        return out
+
+
+_default: dict[int, Engine] = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]
+
+
+# ====================================================================================== reference-named facade
+class AD_Census:
+    """AD-CensusV1/AD-Census.h:9-43 -- same method names and argument order (cv::Mat arguments are accepted and
+    ignored, exactly as the reference only stores them, :329-330)."""
+
+    def __init__(self, engine: Optional[Engine] = None):
+        self._e = engine
+        self._costL = self._costR = None
+
+    def Initialize(self, leftImage, rightImage, dispRange, row, col, LImage=None, RImage=None, sigmaC=10.0, sigmaS=30.0):
+        self._e = self._e or default_engine()
+        self._l = np.ascontiguousarray(leftImage, np.float32).reshape(row, col)
+        self._r = np.ascontiguousarray(rightImage, np.float32).reshape(row, col)
+        self._D, self._sc, self._ss = int(dispRange), float(sigmaC), float(sigmaS)
+        self._costL = self._costR = None
+
+    def ComputeADcensus(self):
+        self._costL = self._e.adcensus_cost(self._l, self._r, self._D, self._sc, self._ss, 0)["cost"]
+
+    def ComputeADcensusRight(self):
+        self._costR = self._e.adcensus_cost(self._l, self._r, self._D, self._sc, self._ss, 1)["cost"]
+
+    def GetPtrLeft(self):
+        return self._costL  # None until computed (the reference returns nullptr, :50-60)
+
+    def GetPtrRight(self):
+        return self._costR
+
+    def WTA(self, leftdisp, rightDisp):
+        leftdisp[...] = self._e.wta(self._costL).reshape(leftdisp.shape)
+        rightDisp[...] = self._e.wta(self._costR).reshape(rightDisp.shape)
+
+
+class CrossAggregator:
+    """CBLSM/cross_aggregator.h:27-113."""
+
+    def __init__(self, engine: Optional[Engine] = None, mode: int = SUM_REFERENCE_ORDER):
+        self._e = engine
+        self._mode = mode
+        self._init = False
+        self._arms = self._cost = None
+        self._params = (34, 17, 20, 6)
+
+    def Initialize(self, width, height, min_disparity, max_disparity) -> bool:
+        self._e = self._e or default_engine()
+        self._w, self._h = int(width), int(height)
+        self._D = int(max_disparity) - int(min_disparity)
+        self._init = self._w * self._h > 0 and self._D > 0  # cross_aggregator.cpp:26-31
+        return self._init
+
+    def SetData(self, img_left, img_right, cost_init):
+        self._img = np.ascontiguousarray(img_left, np.uint8).reshape(self._h, self._w, 3)
+        self._cost_init = np.ascontiguousarray(cost_init, np.float32).reshape(self._h, self._w, self._D)
+
+    def SetParams(self, cross_L1, cross_L2, cross_t1, cross_t2):
+        self._params = (int(cross_L1), int(cross_L2), int(cross_t1), int(cross_t2))
+
+    def Aggregate(self, num_iters):
+        if not self._init:  # silently no-op (:91-93)
+            return
+        r = self._e.aggregate_cross(self._img, self._cost_init, *self._params, iters=int(num_iters), mode=self._mode,
+                                    want_arms=True)
+        self._cost, self._arms = r["cost"], r["arms"]
+        self._sup = (r["sup0"], r["sup1"])
+
+    def get_arms_ptr(self):
+        return self._arms
+
+    def get_cost_ptr(self):
+        return self._cost
+
+
+class ScanlineOptimizer:
+    """AD-CensusV1/ScanlineOptimizer.h:8-34."""
+
+    def __init__(self, engine: Optional[Engine] = None):
+        self._e = engine
+        self._out = {}
+
+    def Initialize(self, row, col, dispRange, costVolume, p1, p2):
+        self._e = self._e or default_engine()
+        self._shape = (int(row), int(col), int(dispRange))
+        self._p1, self._p2 = int(p1), int(p2)  # int parameters (:66)
+
+    def ScanLine(self, costVolume, Image, want=("left", "right", "up", "down", "sum", "disp")):
+        H, W, D = self._shape
+        cost = np.ascontiguousarray(costVolume, np.float32).reshape(H, W, D)
+        gray = np.ascontiguousarray(Image, np.float32).reshape(H, W)
+        self._out = self._e.scanline(cost, gray, self._p1, self._p2, want=want)
+
+    def WTA(self, disp):
+        disp[...] = self._out["disp"].reshape(disp.shape)
+
+    @property
+    def volumes(self):
+        return self._out
+
+
+def LeftRightConsistency(col, row, gate, leftDisp, rightDisp, occlusion: list, mismatch: list, engine=None):
+    """PostProcessing.h:72 -- modifies leftDisp in place, fills the two (row, col) lists."""
+    e = engine or default_engine()
+    d, occ, mis = e.lrcheck(np.asarray(leftDisp, np.float32).reshape(row, col),
+                            np.asarray(rightDisp, np.float32).reshape(row, col), gate)
+    leftDisp[...] = d.reshape(leftDisp.shape)
+    occlusion[:] = [tuple(x) for x in occ.tolist()]
+    mismatch[:] = [tuple(x) for x in mis.tolist()]
+
+
+def LeftAndRightConsistency(leftDisp, rightDisp, lastDisp, col, row, gate, occlusion: list, mismatch: list, engine=None):
+    """PostProcessing.h:10."""
+    e = engine or default_engine()
+    last, occ, mis = e.lrcheck_and(np.asarray(leftDisp, np.float32).reshape(row, col),
+                                   np.asarray(rightDisp, np.float32).reshape(row, col), gate)
+    lastDisp[...] = last.reshape(lastDisp.shape)
+    occlusion.extend(tuple(x) for x in occ.tolist())  # the reference appends without clearing (:44-66)
+    mismatch.extend(tuple(x) for x in mis.tolist())
+
+
+def RemoveSpeckles(disparity_map, width, height, diff_insame, min_speckle_aera, invalid_val, engine=None):
+    """PostProcessing.h:250 -- invalid_val is an int; +inf becomes 2147483647 as under g++."""
+    e = engine or default_engine()
+    if isinstance(invalid_val, float) and np.isinf(invalid_val):
+        invalid_val = INVALID_INT_FROM_INF
+    d = e.remove_speckles(np.asarray(disparity_map, np.float32).reshape(height, width), diff_insame, min_speckle_aera,
+                          int(invalid_val))
+    disparity_map[...] = d.reshape(disparity_map.shape)
+
+
+def MedianFilter(in_, out, width, height, wnd_size, engine=None):
+    """PostProcessing.h:314."""
+    e = engine or default_engine()
+    out[...] = e.median(np.asarray(in_, np.float32).reshape(height, width), wnd_size).reshape(out.shape)

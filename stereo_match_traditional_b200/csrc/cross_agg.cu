@@ -1,0 +1,202 @@
+// Cross-based cost aggregation.
+//
+// Replaces CrossAggregator::{BuildArms, FindHorizontalArm, FindVerticalArm, ComputeSupPixelCount, Aggregate,
+// AggregateInArms} (CBLSM/cross_aggregator.cpp:76-118, :135-394).
+//
+// Arms and support counts are integer work on the image only (one kernel each).  Aggregation is, per iteration and
+// per disparity slice, two 1-D passes: sum along one arm pair, then along the orthogonal pair, divide by the support
+// count; the order alternates per iteration (:102,:116).  The reference gathers one strided slice at a time; here a
+// pass handles all D slices of a pixel together (D innermost => every tap is a coalesced row of the volume).
+//
+// Two summation modes:
+//   SMT_SUM_REFERENCE_ORDER  each cell adds its taps sequentially in the reference's order (t ascending, starting
+//                            from 0.0f, :358-383) -> bit-identical to the reference.
+//   SMT_SUM_FAST             see agg_line_kernel below.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- arms
+__device__ __forceinline__ int color_dist(int b0, int g0, int r0, int b1, int g1, int r1) {
+    return max(abs(r0 - r1), max(abs(g0 - g1), abs(b0 - b1)));  // cross_aggregator.h:78-80
+}
+
+// walks one direction from (x,y); step is the pixel stride of that direction, room the number of in-image pixels
+__device__ __forceinline__ int walk_arm(const uint8_t* __restrict__ p0, long long step, int room, int Lmax, int L2, int t1,
+                                        int t2) {
+    const int b0 = p0[0], g0 = p0[1], r0 = p0[2];
+    int bl = b0, gl = g0, rl = r0;
+    int arm = 0;
+    const uint8_t* p = p0 + step;
+    for (int n = 0; n < Lmax; ++n) {
+        if (n >= room) break;  // border (:154-163)
+        const int b = p[0], g = p[1], r = p[2];
+        const int d1 = color_dist(b, g, r, b0, g0, r0);
+        if (d1 >= t1) break;                                  // :169-172
+        if (n > 0 && color_dist(b, g, r, bl, gl, rl) >= t1) break;  // :175-180
+        if (n + 1 > L2 && d1 >= t2) break;                    // :183-187
+        ++arm;
+        bl = b;
+        gl = g;
+        rl = r;
+        p += step;
+    }
+    return arm;
+}
+
+__global__ void __launch_bounds__(128) cross_arms_kernel(const uint8_t* __restrict__ bgr, int H, int W, int L1, int L2, int t1,
+                                                         int t2, uchar4* __restrict__ arms) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const int Lmax = min(L1, 255);  // MAX_ARM_LENGTH (cross_aggregator.h:24)
+    const uint8_t* p0 = bgr + ((size_t)y * W + x) * 3;
+    uchar4 a;
+    a.x = (unsigned char)walk_arm(p0, -3, x, Lmax, L2, t1, t2);
+    a.y = (unsigned char)walk_arm(p0, 3, W - 1 - x, Lmax, L2, t1, t2);
+    a.z = (unsigned char)walk_arm(p0, -3ll * W, y, Lmax, L2, t1, t2);
+    a.w = (unsigned char)walk_arm(p0, 3ll * W, H - 1 - y, Lmax, L2, t1, t2);
+    arms[(size_t)y * W + x] = a;
+}
+
+// sup_hfirst(y,x) = sum_{t=-top..bottom} (left+right+1)(y+t,x);  sup_vfirst(y,x) = sum_{t=-left..right} (top+bottom+1)(y,x+t)
+// (cross_aggregator.cpp:271-325; uint16 storage as in the reference).
+__global__ void __launch_bounds__(128) support_count_kernel(const uchar4* __restrict__ arms, int H, int W,
+                                                            uint16_t* __restrict__ sup0, uint16_t* __restrict__ sup1) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const uchar4 a = arms[(size_t)y * W + x];
+    int c0 = 0, c1 = 0;
+    for (int t = -(int)a.z; t <= (int)a.w; ++t) {
+        const uchar4 b = arms[(size_t)(y + t) * W + x];
+        c0 += (int)(uint16_t)(b.x + b.y + 1);
+    }
+    for (int t = -(int)a.x; t <= (int)a.y; ++t) {
+        const uchar4 b = arms[(size_t)y * W + x + t];
+        c1 += (int)(uint16_t)(b.z + b.w + 1);
+    }
+    if (sup0) sup0[(size_t)y * W + x] = (uint16_t)c0;
+    if (sup1) sup1[(size_t)y * W + x] = (uint16_t)c1;
+}
+
+smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1, int L2, int t1, int t2, uint8_t* arms,
+                          uint16_t* sup0, uint16_t* sup1) {
+    StageTimer t(ctx, ST_ARMS);
+    dim3 grid(cdiv(W, 128), H);
+    SMT_LAUNCH(ctx, cross_arms_kernel, grid, 128, 0, bgr, H, W, L1, L2, t1, t2, reinterpret_cast<uchar4*>(arms));
+    if (sup0 || sup1)
+        SMT_LAUNCH(ctx, support_count_kernel, grid, 128, 0, reinterpret_cast<const uchar4*>(arms), H, W, sup0, sup1);
+    return SMT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- reference-order passes
+// One thread per (pixel, d), d fastest.  HORIZ: taps (y, x+t), t=-left..right; else (y+t, x), t=-top..bottom.
+// sup != nullptr => second pass of an iteration: divide by the support count (float / int, IEEE division, :389).
+template <bool HORIZ>
+__global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                             const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
+                                                             int H, int W, int D) {
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ncell = (size_t)H * W * D;
+    if (cell >= ncell) return;
+    const size_t pix = cell / D;
+    const int d = (int)(cell - pix * D);
+    const uchar4 a = arms[pix];
+    const int lo = HORIZ ? -(int)a.x : -(int)a.z;
+    const int hi = HORIZ ? (int)a.y : (int)a.w;
+    const long long step = HORIZ ? (long long)D : (long long)W * D;
+    const float* p = in + (long long)pix * D + d + lo * step;
+    float acc = 0.0f;
+    for (int t = lo; t <= hi; ++t) {
+        acc = __fadd_rn(acc, *p);
+        p += step;
+    }
+    if (sup) acc = __fdiv_rn(acc, (float)(int)sup[pix]);
+    out[cell] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------- fast line passes
+// (implemented in cross_agg_fast.cu)
+smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float** result);
+
+smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
+                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float** result) {
+    if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, result);
+    StageTimer t(ctx, ST_AGGREGATE);
+    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    const size_t ncell = (size_t)H * W * D;
+    const unsigned grid = cdiv((long long)ncell, 256);
+    bool hfirst = true;
+    float* cur = vol;
+    float* oth = tmp;
+    for (int k = 0; k < iters; ++k) {
+        if (hfirst) {
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, cur, oth, arms, (const uint16_t*)nullptr, H, W, D);
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, oth, cur, arms, sup0, H, W, D);
+        } else {
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, cur, oth, arms, (const uint16_t*)nullptr, H, W, D);
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, oth, cur, arms, sup1, H, W, D);
+        }
+        hfirst = !hfirst;
+    }
+    *result = cur;  // every iteration ends back in `vol`
+    return SMT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+smt_status_t smt_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int32_t cols, int32_t L1, int32_t L2, int32_t t1,
+                            int32_t t2, uint8_t* arms_out, uint16_t* sup_hfirst, uint16_t* sup_vfirst, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, bgr && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_cross_arms: bad argument");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)rows * cols;
+    Marshal ms(ctx, space);
+    const uint8_t* dbgr = ms.in(bgr, npix * 3);
+    uint8_t* darms = ms.out(arms_out, npix * 4);
+    uint16_t* ds0 = ms.out(sup_hfirst, npix);
+    uint16_t* ds1 = ms.out(sup_vfirst, npix);
+    SMT_TRY(ms.check());
+    SMT_ALLOC(ctx, tmp_arms, darms ? 0 : npix * 4);
+    if (!darms) darms = tmp_arms.as<uint8_t>();
+    SMT_TRY(k_cross_arms(ctx, dbgr, rows, cols, L1, L2, t1, t2, darms, ds0, ds1));
+    return ms.finish();
+}
+
+smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const float* cost_init, int32_t rows, int32_t cols, int32_t D,
+                                 int32_t L1, int32_t L2, int32_t t1, int32_t t2, int32_t iters, smt_sum_mode_t mode,
+                                 float* cost_out, uint8_t* arms_out, uint16_t* sup_hfirst, uint16_t* sup_vfirst,
+                                 smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, bgr && cost_init && cost_out && rows > 0 && cols > 0 && D > 0 && iters >= 0, SMT_ERR_INVALID_ARG,
+                "smt_aggregate_cross: bad argument");
+    SMT_REQUIRE(ctx, mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST, SMT_ERR_INVALID_ARG,
+                "smt_aggregate_cross: unknown sum mode");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)rows * cols, nvol = npix * D;
+    Marshal ms(ctx, space);
+    const uint8_t* dbgr = ms.in(bgr, npix * 3);
+    const float* dinit = ms.in(cost_init, nvol);
+    float* dout = ms.out(cost_out, nvol);
+    uint8_t* darms = ms.out(arms_out, npix * 4);
+    uint16_t* ds0 = ms.out(sup_hfirst, npix);
+    uint16_t* ds1 = ms.out(sup_vfirst, npix);
+    SMT_TRY(ms.check());
+    SMT_ALLOC(ctx, aux, npix * 8);  // arms (4 B) + two uint16 maps when the caller does not want them
+    if (!darms) darms = aux.as<uint8_t>();
+    if (!ds0) ds0 = reinterpret_cast<uint16_t*>(aux.as<uint8_t>() + npix * 4);
+    if (!ds1) ds1 = reinterpret_cast<uint16_t*>(aux.as<uint8_t>() + npix * 6);
+    SMT_ALLOC(ctx, tmp, nvol * sizeof(float));
+    SMT_TRY(k_cross_arms(ctx, dbgr, rows, cols, L1, L2, t1, t2, darms, ds0, ds1));
+    // the reference memcpy's cost_init into its own volume first (:108)
+    if (dout != dinit)
+        SMT_CUDA(ctx, cudaMemcpyAsync(dout, dinit, nvol * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    float* res = nullptr;
+    SMT_TRY(k_aggregate_cross(ctx, dout, tmp.as<float>(), darms, ds0, ds1, rows, cols, D, iters, mode, &res));
+    if (res != dout)
+        SMT_CUDA(ctx, cudaMemcpyAsync(dout, res, nvol * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return ms.finish();
+}
+
+}  // extern "C"

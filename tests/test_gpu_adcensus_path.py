@@ -1,0 +1,140 @@
+"""GPU parity of the AD-Census hot path (cost, aggregation, scanline, post-processing, P_full) against the oracle.
+
+Bars (BASELINE.json north_star): bit-exact for census/Hamming/AD/cost LUT, WTA, LR check; SMT_SUM_REFERENCE_ORDER
+aggregation and the scanline are bit-exact too (same operation order); SMT_SUM_FAST is held to rel. err <= 1e-5.
+"""
+import numpy as np
+import pytest
+
+from stereo_match_traditional_b200.synth import make_pair
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (H, W, D, kind, seed)
+    (48, 200, 24, "scene", 7),
+    (33, 257, 40, "scene", 8),
+    (64, 64, 16, "noise", 9),
+    (40, 96, 128, "scene", 10),   # D > W
+    (24, 50, 7, "noise", 11),     # D % 4 != 0 -> scalar paths
+    (30, 70, 32, "constant", 12),
+]
+
+
+@pytest.mark.parametrize("H,W,D,kind,seed", SHAPES)
+def test_adcensus_cost_bit_exact(engine, oracle, H, W, D, kind, seed):
+    p = make_pair(H, W, D, seed, kind)
+    L = p["gray_left"].astype(np.float32)
+    R = p["gray_right"].astype(np.float32)
+    ref = oracle.adcensus(L, R, D, want=("costL", "costR", "adL", "adR", "censusL", "censusR", "wtaL", "wtaR"))
+    for view, s in ((0, "L"), (1, "R")):
+        got = engine.adcensus_cost(L, R, D, 10.0, 30.0, view, want_ad=True, want_census=True)
+        assert np.array_equal(got["ad"], ref["ad" + s]), f"AD view {view}"
+        assert np.array_equal(got["census"], ref["census" + s]), f"Hamming view {view}"
+        assert np.array_equal(got["cost"], ref["cost" + s]), f"cost view {view}"
+        assert np.array_equal(engine.wta(got["cost"]), ref["wta" + s]), f"WTA view {view}"
+
+
+def test_census_bitstring_matches_hamming(engine, oracle):
+    """popcount(census_u64(L) ^ census_u64(R shifted)) reproduces the reference Hamming volume at interior pixels."""
+    H, W, D = 40, 120, 8
+    p = make_pair(H, W, D, 21, "noise")
+    L = p["gray_left"].astype(np.float32)
+    R = p["gray_right"].astype(np.float32)
+    cl = engine.census9x7(L)
+    cr = engine.census9x7(R)
+    ref = oracle.adcensus(L, R, D, want=("censusL",))["censusL"]
+    pop = np.vectorize(lambda v: bin(int(v)).count("1"))
+    for d in (0, 3, 7):
+        x = np.arange(3 + d, W - 3)
+        ham = pop(cl[4:H - 4][:, x] ^ cr[4:H - 4][:, x - d])
+        assert np.array_equal(ham.astype(np.float32), ref[4:H - 4][:, x, d])
+
+
+@pytest.mark.parametrize("H,W,D,kind,seed", SHAPES[:5])
+def test_cross_aggregate_reference_order_bit_exact(engine, oracle, H, W, D, kind, seed):
+    p = make_pair(H, W, D, seed, kind)
+    rng = np.random.default_rng(seed)
+    cost = rng.random((H, W, D), dtype=np.float32) * 2
+    ref = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], cost)
+    got = engine.aggregate_cross(p["bgr_left"], cost, want_arms=True)
+    assert np.array_equal(got["arms"], ref["arms"])
+    assert np.array_equal(got["sup0"], ref["sup0"])
+    assert np.array_equal(got["sup1"], ref["sup1"])
+    assert np.array_equal(got["cost"], ref["cost"])
+
+
+@pytest.mark.parametrize("H,W,D,kind,seed", SHAPES[:5])
+def test_scanline_bit_exact(engine, oracle, H, W, D, kind, seed):
+    p = make_pair(H, W, D, seed, kind)
+    rng = np.random.default_rng(seed + 100)
+    cost = rng.random((H, W, D), dtype=np.float32) * 2
+    gray = p["gray_left"].astype(np.float32)
+    names = ("left", "right", "up", "down", "sum", "disp")
+    ref = oracle.scanline(cost, gray, 10, 150, want=names)
+    got = engine.scanline(cost, gray, 10, 150, want=names)
+    for n in names:
+        assert np.array_equal(got[n], ref[n]), n
+    # fused variant (no path volumes): same disparity
+    got2 = engine.scanline(cost, gray, 10, 150, want=("disp",))
+    assert np.array_equal(got2["disp"], ref["disp"])
+
+
+def _disp_pair(H, W, D, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, D, (H, 1)).astype(np.float32) + np.zeros((H, W), np.float32)
+    dl = base + rng.integers(-1, 2, (H, W))
+    dl[rng.random((H, W)) < 0.08] = rng.integers(0, D)
+    dr = base + rng.integers(-1, 2, (H, W))
+    dr[rng.random((H, W)) < 0.08] = rng.integers(0, D)
+    return np.clip(dl, 0, D - 1).astype(np.float32), np.clip(dr, 0, D - 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("H,W,D,seed", [(40, 120, 32, 1), (37, 301, 64, 2), (8, 16, 20, 3)])
+def test_postprocessing_bit_exact(engine, oracle, H, W, D, seed):
+    dl, dr = _disp_pair(H, W, D, seed)
+    dl[0, :3] = np.inf  # already-invalid inputs take the :90 branch
+    rd, rocc, rmis = oracle.lrcheck(dl, dr, 2)
+    gd, gocc, gmis = engine.lrcheck(dl, dr, 2)
+    assert np.array_equal(gd, rd)
+    assert np.array_equal(gocc, rocc) and np.array_equal(gmis, rmis)
+    rl, rocc2, rmis2 = oracle.lrcheck_and(dl[1:], dr[1:], 2.0)
+    gl, gocc2, gmis2 = engine.lrcheck_and(dl[1:], dr[1:], 2.0)
+    assert np.array_equal(gl, rl)
+    assert np.array_equal(gocc2, rocc2) and np.array_equal(gmis2, rmis2)
+    # speckles: the shipped call (invalid = +inf -> 2147483647) and a plain integer sentinel
+    rs = oracle.remove_speckles(rd, 1, 30, None)
+    gs = engine.remove_speckles(gd, 1, 30)
+    assert np.array_equal(gs, rs)
+    rs2 = oracle.remove_speckles(dl[1:], 1, 12, -1)
+    gs2 = engine.remove_speckles(dl[1:], 1, 12, -1)
+    assert np.array_equal(gs2, rs2)
+    for k in (3, 5):
+        assert np.array_equal(engine.median(gs, k), oracle.median(rs, k))
+
+
+def oracle_pfull(oracle, p, D):
+    """P_full from the oracle's stage functions."""
+    L = p["gray_left"].astype(np.float32)
+    R = p["gray_right"].astype(np.float32)
+    c = oracle.adcensus(L, R, D, want=("costL", "costR"))
+    aggL = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], c["costL"])["cost"]
+    aggR = oracle.cross_aggregate(p["bgr_right"], p["bgr_left"], c["costR"])["cost"]
+    sl = oracle.scanline(aggL, L, 10, 150, want=("disp",))["disp"]
+    dr = oracle.wta(aggR)
+    lrc, _, _ = oracle.lrcheck(sl, dr, 2)
+    spk = oracle.remove_speckles(lrc, 1, 30, None)
+    return {"left_raw": sl, "right_raw": dr, "lrc": lrc, "disp": oracle.median(spk, 3)}
+
+
+@pytest.mark.parametrize("H,W,D,kind,seed", [(48, 200, 24, "scene", 31), (60, 90, 32, "noise", 32), (45, 130, 20, "scene", 33)])
+def test_pipeline_reference_order_bit_exact(engine, oracle, H, W, D, kind, seed):
+    p = make_pair(H, W, D, seed, kind)
+    ref = oracle_pfull(oracle, p, D)
+    got = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"],
+                          want=("disp", "left_raw", "right_raw", "lrc"))
+    for n in ("right_raw", "left_raw", "lrc", "disp"):
+        assert np.array_equal(got[n], ref[n]), n
+    # gray computed on the device from BGR (cvtColor fixed-point formula) gives the same answer
+    got2 = engine.pipeline(p["bgr_left"], p["bgr_right"], D)
+    assert np.array_equal(got2["disp"], ref["disp"])
