@@ -71,16 +71,27 @@ class Oracle:
         self.kind = kind
         self.prefix = "orc_" if kind == "port" else "ref_"
         self.lib = C.CDLL(str(path))
-        self._fn("remove_speckles").argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int]
-        self._fn("ncc_cost").restype = C.c_double
-        self._fn("sad_optimal_disparity").restype = C.c_float
-        self._fn("asw").argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
-                                    C.c_int, _f32p]
-        self._fn("asw_masks").argtypes = [C.c_int, C.c_double, C.c_double, _f64p, _f64p]
-        self._fn("adcensus").argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
-                                         C.c_int] + [_f32p] * 8
-        self._fn("lrcheck_and").argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, _i32p, _i32p, _i32p,
-                                            _i32p]
+        # symbols are attached only when the library exports them (the C port grows stage by stage)
+        def sig(name, argtypes=None, restype=None):
+            try:
+                fn = self._fn(name)
+            except AttributeError:
+                return
+            if argtypes is not None:
+                fn.argtypes = argtypes
+            if restype is not None:
+                fn.restype = restype
+
+        sig("remove_speckles", [_f32p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int])
+        sig("ncc_cost", restype=C.c_double)
+        sig("sad_optimal_disparity", restype=C.c_float)
+        sig("asw", [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _f32p])
+        sig("asw_masks", [C.c_int, C.c_double, C.c_double, _f64p, _f64p])
+        sig("adcensus", [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int] + [_f32p] * 8)
+        sig("lrcheck_and", [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, _i32p, _i32p, _i32p, _i32p])
+
+    def has(self, name: str) -> bool:
+        return hasattr(self.lib, self.prefix + name)
 
     def _fn(self, name):
         return getattr(self.lib, self.prefix + name)

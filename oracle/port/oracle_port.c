@@ -1,0 +1,462 @@
+/* ORACLE (test infrastructure, never shipped, never on the product path).
+ *
+ * Plain-C restatement of the reference's hot-path algorithms; see oracle_port.h for the parity status.
+ * Each function cites the reference file:line it restates.  Floating-point code keeps the reference's
+ * operation order and types (build with -ffp-contract=off, no -ffast-math) so results are bit-identical.
+ */
+#include "oracle_port.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+int orc_abi_version(void) { return 1; }
+int orc_num_threads(void) { return 1; }
+
+#define VOL(i, j, d) ((((size_t)(i)) * W + (size_t)(j)) * D + (size_t)(d))
+
+/* ------------------------------------------------------------------------------------------------ AD-Census
+ * AD-CensusV1/AD-Census.h.  Images are float arrays holding grey levels. */
+
+/* ComputeAD (:75-101) / ComputeADRight (:103-129): an out-of-range match copies the previous disparity's cost,
+ * which is the clamped match. */
+static void ad_volume(const float* own, const float* oth, int H, int W, int D, int sign, float* out) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const float v = own[(size_t)i * W + j];
+            for (int d = 0; d < D; ++d) {
+                const int x = j + sign * d;
+                if (x < 0 || x >= W) {
+                    out[VOL(i, j, d)] = out[VOL(i, j, d - 1)]; /* :88-92, :116-120 */
+                } else {
+                    const float o = oth[(size_t)i * W + x];
+                    /* left view: |L - R| (:96); right view: |L - R| with L the shifted one (:124) */
+                    out[VOL(i, j, d)] = sign < 0 ? fabsf(v - o) : fabsf(o - v);
+                }
+            }
+        }
+}
+
+/* ComputeCensus9x7 (:142-204, right = 0) and ComputeCensus9x7Right (:207-269, right = 1).
+ * Both 63-tap strings are rebuilt for every (pixel, d); a tap is skipped (bit 0 in both strings) when it
+ * leaves the image in the ANCHOR's frame (:173, :238).  Left view: the right image's centre and taps clamp to
+ * column 0 (:159-164, :177-182).  Right view: the left centre clamps to column W-1 (:224-229) but an
+ * overflowing tap reads column 0 (:242-243). */
+static void census_volume(const float* L, const float* R, int H, int W, int D, int right, float* out) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const float own_c = right ? R[(size_t)i * W + j] : L[(size_t)i * W + j];
+            for (int d = 0; d < D; ++d) {
+                float oth_c;
+                if (!right)
+                    oth_c = (j - d < 0) ? R[(size_t)i * W] : R[(size_t)i * W + j - d];
+                else
+                    oth_c = (j + d >= W) ? L[(size_t)i * W + W - 1] : L[(size_t)i * W + j + d];
+                uint64_t a = 0, b = 0;
+                for (int r = -4; r <= 4; ++r)
+                    for (int c = -3; c <= 3; ++c) {
+                        a <<= 1;
+                        b <<= 1;
+                        const int y = i + r, x = j + c;
+                        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+                        float own_t, oth_t;
+                        if (!right) {
+                            own_t = L[(size_t)y * W + x];
+                            oth_t = (x - d < 0) ? R[(size_t)y * W] : R[(size_t)y * W + x - d];
+                        } else {
+                            own_t = R[(size_t)y * W + x];
+                            oth_t = (x + d >= W) ? L[(size_t)y * W] : L[(size_t)y * W + x + d];
+                        }
+                        if (own_c > own_t) a += 1;
+                        if (oth_c > oth_t) b += 1;
+                    }
+                uint64_t x = a ^ b;
+                int n = 0;
+                while (x) { /* :194-198 */
+                    ++n;
+                    x &= x - 1;
+                }
+                out[VOL(i, j, d)] = (float)n;
+            }
+        }
+}
+
+/* first-minimum WTA with a strict comparison (:346-380; CrossArm.cpp:33-57; ScanlineOptimizer.h:40-64) */
+void orc_wta(const float* vol, int H, int W, int D, float* disp) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float best = vol[VOL(i, j, 0)];
+            float bd = 0;
+            for (int d = 1; d < D; ++d) {
+                const float v = vol[VOL(i, j, d)];
+                if (best > v) {
+                    best = v;
+                    bd = (float)d;
+                }
+            }
+            disp[(size_t)i * W + j] = bd;
+        }
+}
+
+void orc_adcensus(const float* left, const float* right, int H, int W, int D, float sigmaC, float sigmaS, int do_left,
+                  int do_right, float* costL, float* costR, float* adL, float* adR, float* censusL, float* censusR,
+                  float* wtaL, float* wtaR) {
+    const size_t n = (size_t)H * W * D;
+    float* out_cost[2] = {costL, costR};
+    float* out_ad[2] = {adL, adR};
+    float* out_cen[2] = {censusL, censusR};
+    float* out_wta[2] = {wtaL, wtaR};
+    const int doit[2] = {do_left, do_right};
+    for (int v = 0; v < 2; ++v) {
+        if (!doit[v]) {
+            /* Initialize zero-fills every volume (:334-342); WTA of an all-zero volume is 0 */
+            if (out_cost[v]) memset(out_cost[v], 0, n * sizeof(float));
+            if (out_ad[v]) memset(out_ad[v], 0, n * sizeof(float));
+            if (out_cen[v]) memset(out_cen[v], 0, n * sizeof(float));
+            if (wtaL && wtaR) memset(out_wta[v], 0, (size_t)H * W * sizeof(float));
+            continue;
+        }
+        float* ad = (float*)malloc(n * sizeof(float));
+        float* cen = (float*)malloc(n * sizeof(float));
+        float* cost = (float*)malloc(n * sizeof(float));
+        if (v == 0)
+            ad_volume(left, right, H, W, D, -1, ad);
+        else
+            ad_volume(right, left, H, W, D, +1, ad);
+        census_volume(left, right, H, W, D, v, cen);
+        for (size_t k = 0; k < n; ++k) {
+            /* ComputeADcensus (:287-289): every operation in float32 (std::exp(float)) */
+            const float a = 1 - expf(-(ad[k] / sigmaC));
+            const float c = 1 - expf(-(cen[k] / sigmaS));
+            cost[k] = a + c;
+        }
+        if (wtaL && wtaR) orc_wta(cost, H, W, D, out_wta[v]);
+        if (out_cost[v]) memcpy(out_cost[v], cost, n * sizeof(float));
+        if (out_ad[v]) memcpy(out_ad[v], ad, n * sizeof(float));
+        if (out_cen[v]) memcpy(out_cen[v], cen, n * sizeof(float));
+        free(ad);
+        free(cen);
+        free(cost);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ CrossAggregator
+ * CBLSM/cross_aggregator.cpp */
+static int cdist(const uint8_t* a, const uint8_t* b) { /* cross_aggregator.h:78-80 */
+    int m = abs((int)a[0] - (int)b[0]);
+    const int g = abs((int)a[1] - (int)b[1]), r = abs((int)a[2] - (int)b[2]);
+    if (g > m) m = g;
+    if (r > m) m = r;
+    return m;
+}
+
+/* FindHorizontalArm / FindVerticalArm (:135-269): step = +-1 pixel or +-W pixels, room = pixels before the border */
+static uint8_t grow_arm(const uint8_t* img, size_t p0, long step, int room, int L1, int L2, int t1, int t2) {
+    const int lim = L1 < 255 ? L1 : 255; /* min(cross_L1_, MAX_ARM_LENGTH) (:151) */
+    const uint8_t* c0 = img + 3 * p0;
+    const uint8_t* last = c0;
+    int arm = 0;
+    for (int n = 0; n < lim; ++n) {
+        if (n >= room) break; /* :154-163 */
+        const uint8_t* c = img + 3 * (size_t)((long)p0 + step * (n + 1));
+        const int d1 = cdist(c, c0);
+        if (d1 >= t1) break;                    /* :169-172 */
+        if (n > 0 && cdist(c, last) >= t1) break; /* :175-180 */
+        if (n + 1 > L2 && d1 >= t2) break;      /* :183-187 */
+        ++arm;
+        last = c;
+    }
+    return (uint8_t)arm;
+}
+
+int orc_cross_aggregate(const uint8_t* bgrL, const uint8_t* bgrR, const float* cost_init, int W, int H, int D, int L1,
+                        int L2, int t1, int t2, int iters, float* cost_out, uint8_t* arms_out, uint16_t* sup0_out,
+                        uint16_t* sup1_out) {
+    (void)bgrR; /* only img_left_ is read (:138,:206) */
+    const size_t npix = (size_t)W * H;
+    if ((long)W * H <= 0 || D <= 0) return 0; /* Initialize (:26-31) */
+    uint8_t* arms = (uint8_t*)malloc(npix * 4);
+    uint16_t* sup[2] = {(uint16_t*)malloc(npix * 2), (uint16_t*)malloc(npix * 2)};
+    uint16_t* suptmp = (uint16_t*)malloc(npix * 2);
+    float* t0 = (float*)malloc(npix * sizeof(float));
+    float* t1v = (float*)malloc(npix * sizeof(float));
+    float* agg = (float*)malloc(npix * D * sizeof(float));
+    /* BuildArms (:76-86) */
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t p = (size_t)y * W + x;
+            arms[4 * p + 0] = grow_arm(bgrL, p, -1, x, L1, L2, t1, t2);
+            arms[4 * p + 1] = grow_arm(bgrL, p, +1, W - 1 - x, L1, L2, t1, t2);
+            arms[4 * p + 2] = grow_arm(bgrL, p, -(long)W, y, L1, L2, t1, t2);
+            arms[4 * p + 3] = grow_arm(bgrL, p, +(long)W, H - 1 - y, L1, L2, t1, t2);
+        }
+    /* ComputeSupPixelCount (:271-325): id 0 = horizontal first, id 1 = vertical first */
+    for (int id = 0; id < 2; ++id)
+        for (int pass = 0; pass < 2; ++pass)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    const size_t p = (size_t)y * W + x;
+                    const int l = arms[4 * p], r = arms[4 * p + 1], t = arms[4 * p + 2], b = arms[4 * p + 3];
+                    const int horizontal = (id == 0) == (pass == 0);
+                    int count = 0;
+                    if (pass == 0) {
+                        count = horizontal ? (l + r + 1) : (t + b + 1);
+                        suptmp[p] = (uint16_t)count;
+                    } else {
+                        if (horizontal)
+                            for (int s = -l; s <= r; ++s) count += suptmp[p + s];
+                        else
+                            for (int s = -t; s <= b; ++s) count += suptmp[(size_t)(y + s) * W + x];
+                        sup[id][p] = (uint16_t)count;
+                    }
+                }
+    /* Aggregate (:89-118) */
+    memcpy(agg, cost_init, npix * D * sizeof(float));
+    int hfirst = 1;
+    for (int k = 0; k < iters; ++k) {
+        for (int d = 0; d < D; ++d) {
+            /* AggregateInArms (:327-394) */
+            for (size_t p = 0; p < npix; ++p) t0[p] = agg[p * D + d];
+            for (int pass = 0; pass < 2; ++pass)
+                for (int y = 0; y < H; ++y)
+                    for (int x = 0; x < W; ++x) {
+                        const size_t p = (size_t)y * W + x;
+                        const int horizontal = (hfirst != 0) == (pass == 0);
+                        const float* src = pass == 0 ? t0 : t1v;
+                        float acc = 0.0f;
+                        if (horizontal)
+                            for (int s = -(int)arms[4 * p]; s <= (int)arms[4 * p + 1]; ++s) acc += src[p + s];
+                        else
+                            for (int s = -(int)arms[4 * p + 2]; s <= (int)arms[4 * p + 3]; ++s)
+                                acc += src[(size_t)(y + s) * W + x];
+                        if (pass == 0)
+                            t1v[p] = acc;
+                        else
+                            agg[p * D + d] = acc / sup[hfirst ? 0 : 1][p]; /* float / int(uint16) (:389) */
+                    }
+        }
+        hfirst = !hfirst;
+    }
+    if (cost_out) memcpy(cost_out, agg, npix * D * sizeof(float));
+    if (arms_out) memcpy(arms_out, arms, npix * 4);
+    if (sup0_out) memcpy(sup0_out, sup[0], npix * 2);
+    if (sup1_out) memcpy(sup1_out, sup[1], npix * 2);
+    free(arms);
+    free(sup[0]);
+    free(sup[1]);
+    free(suptmp);
+    free(t0);
+    free(t1v);
+    free(agg);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ ScanlineOptimizer
+ * AD-CensusV1/ScanlineOptimizer.h */
+static float fmin2(float a, float b) { return b < a ? b : a; } /* std::min */
+
+/* One path: n pixels starting at pixel p0 with pixel stride pstep; grey values start at g0 with stride gstep.
+ * vertical != 0 selects the up/down variant: reference grey fixed at the start pixel (:210,:232), l2 = prev[d]+p1 (:238). */
+static void scan_one_path(const float* cost, const float* gray, int D, long p0, long pstep, long g0, long gstep, int n,
+                          float p1, float p2init, int vertical, float* out, float* prev /* D+2 */) {
+    for (int d = 0; d < D + 2; ++d) prev[d] = 65535.f; /* 0xffff (:151,:213) */
+    memcpy(out + (size_t)p0 * D, cost + (size_t)p0 * D, (size_t)D * sizeof(float)); /* :153,:215 */
+    memcpy(prev + 1, out + (size_t)p0 * D, (size_t)D * sizeof(float));
+    float m = 65535.f;
+    for (int d = 0; d < D + 2; ++d) m = fmin2(prev[d], m); /* :162-166 */
+    float glast = gray[g0];
+    for (int s = 1; s < n; ++s) {
+        const long p = p0 + pstep * s;
+        const float g = gray[g0 + gstep * s];
+        float q = p2init / (fabsf(g - glast) + 1); /* :171,:232 */
+        const float p2 = p1 > q ? p1 : q;          /* std::max(p1, ...) */
+        if (!vertical) glast = g;                  /* :172 (never updated in up/down) */
+        float mc = 65535.f;
+        float* o = out + (size_t)p * D;
+        const float* c = cost + (size_t)p * D;
+        for (int d = 0; d < D; ++d) {
+            const float l1 = prev[d + 1];
+            const float l2 = (vertical ? prev[d + 1] : prev[d]) + p1; /* :238 vs :177 */
+            const float l3 = prev[d + 2] + p1;
+            const float l4 = m + p2;
+            const float v = c[d] + fmin2(fmin2(l1, l2), fmin2(l3, l4)) - m; /* :180,:241 */
+            o[d] = v;
+            mc = fmin2(mc, v);
+        }
+        m = mc;
+        memcpy(prev + 1, o, (size_t)D * sizeof(float));
+    }
+}
+
+void orc_scanline(const float* cost, const float* gray, int H, int W, int D, int p1i, int p2i, float* left,
+                  float* right, float* up, float* down, float* sum, float* disp) {
+    if (H <= 0 || W <= 0 || D <= 0) return;
+    const size_t n = (size_t)H * W * D;
+    const float p1 = (float)p1i, p2 = (float)p2i; /* int members (:66,:132-133) */
+    float* vol[4];
+    float* user[4] = {left, right, up, down};
+    for (int k = 0; k < 4; ++k) vol[k] = (float*)calloc(n, sizeof(float));
+    float* prev = (float*)malloc((size_t)(D + 2) * sizeof(float));
+    for (int i = 0; i < H; ++i) { /* ScanLineLeftRight (:130-192) */
+        scan_one_path(cost, gray, D, (long)i * W, +1, (long)i * W, +1, W, p1, p2, 0, vol[0], prev);
+        scan_one_path(cost, gray, D, (long)i * W + W - 1, -1, (long)i * W + W - 1, -1, W, p1, p2, 0, vol[1], prev);
+    }
+    for (int j = 0; j < W; ++j) { /* ScanLineUpDown (:194-253): grey pointer moves by +-1 element (:221,:250) */
+        scan_one_path(cost, gray, D, j, +W, j, +1, H, p1, p2, 1, vol[2], prev);
+        scan_one_path(cost, gray, D, (long)(H - 1) * W + j, -W, (long)(H - 1) * W + j, -1, H, p1, p2, 1, vol[3], prev);
+    }
+    float* s = (float*)malloc(n * sizeof(float));
+    for (size_t k = 0; k < n; ++k) s[k] = vol[0][k] + vol[1][k] + vol[2][k] + vol[3][k]; /* :124 */
+    if (disp) orc_wta(s, H, W, D, disp);
+    if (sum) memcpy(sum, s, n * sizeof(float));
+    for (int k = 0; k < 4; ++k) {
+        if (user[k]) memcpy(user[k], vol[k], n * sizeof(float));
+        free(vol[k]);
+    }
+    free(s);
+    free(prev);
+}
+
+/* ------------------------------------------------------------------------------------------------ PostProcessing.h */
+static void push_pair(int32_t* list, int32_t* n, int i, int j) {
+    if (list) {
+        list[2 * (size_t)*n] = i;
+        list[2 * (size_t)*n + 1] = j;
+    }
+    ++*n;
+}
+
+/* LeftRightConsistency (:72-135): in place, row-major, +inf marks invalid */
+void orc_lrcheck(float* dispL, const float* dispR, int W, int H, int gate, int32_t* occ, int32_t* n_occ, int32_t* mis,
+                 int32_t* n_mis) {
+    int32_t no = 0, nm = 0;
+    const float thr = (float)gate;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float* d = &dispL[(size_t)i * W + j];
+            if (*d == INFINITY) { /* :90-93 */
+                push_pair(mis, &nm, i, j);
+                continue;
+            }
+            const int cr = (int)(j - *d + 0.5); /* :96 */
+            if (cr >= 0 && cr < W) {
+                const float dr = dispR[(size_t)i * W + cr];
+                if (fabsf(*d - dr) > thr) { /* :103 */
+                    const int crl = (int)(cr + dr + 0.5); /* :110 */
+                    if (crl > 0 && crl < W) {
+                        if (dispL[(size_t)i * W + crl] > *d) /* reads the array being modified (:112) */
+                            push_pair(occ, &no, i, j);
+                        else
+                            push_pair(mis, &nm, i, j);
+                    } else {
+                        push_pair(mis, &nm, i, j);
+                    }
+                    *d = INFINITY;
+                }
+            } else {
+                *d = INFINITY; /* :130 */
+                push_pair(mis, &nm, i, j);
+            }
+        }
+    if (n_occ) *n_occ = no;
+    if (n_mis) *n_mis = nm;
+}
+
+/* LeftAndRightConsistency (:10-70): separate output, >= gate, no +inf test */
+void orc_lrcheck_and(const float* dispL, const float* dispR, float* last, int W, int H, float gate, int32_t* occ,
+                     int32_t* n_occ, int32_t* mis, int32_t* n_mis) {
+    int32_t no = 0, nm = 0;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const float d = dispL[(size_t)i * W + j];
+            float* lv = &last[(size_t)i * W + j];
+            const int cr = (int)(j - d + 0.5); /* :25 */
+            if (cr >= 0 && cr < W) {
+                const float dr = dispR[(size_t)i * W + cr];
+                if (fabsf(d - dr) >= gate) { /* :33 */
+                    const int crl = (int)(cr + dr + 0.5);
+                    if (crl > 0 && crl < W) {
+                        if (dispL[(size_t)i * W + crl] > d)
+                            push_pair(occ, &no, i, j);
+                        else
+                            push_pair(mis, &nm, i, j);
+                    } else {
+                        push_pair(mis, &nm, i, j);
+                    }
+                    *lv = 0;
+                } else {
+                    *lv = d;
+                }
+            } else {
+                *lv = 0;
+                push_pair(mis, &nm, i, j);
+            }
+        }
+    if (n_occ) *n_occ = no;
+    if (n_mis) *n_mis = nm;
+}
+
+/* RemoveSpeckles (:250-311): breadth-first region growing over the 8-neighbourhood */
+void orc_remove_speckles(float* disp, int W, int H, int diff, unsigned min_area, int invalid_val) {
+    if (W <= 0 || H <= 0) return;
+    const size_t n = (size_t)W * H;
+    unsigned char* seen = (unsigned char*)calloc(n, 1);
+    int32_t* queue = (int32_t*)malloc(n * sizeof(int32_t));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const size_t p = (size_t)i * W + j;
+            if (seen[p] || disp[p] == invalid_val) continue; /* float == int (:262) */
+            size_t head = 0, tail = 0;
+            queue[tail++] = (int32_t)p;
+            seen[p] = 1;
+            while (head < tail) {
+                const int32_t q = queue[head++];
+                const int r0 = q / W, c0 = q % W;
+                const float base = disp[q];
+                for (int r = -1; r <= 1; ++r)
+                    for (int c = -1; c <= 1; ++c) {
+                        if (r == 0 && c == 0) continue;
+                        const int rr = r0 + r, cc = c0 + c;
+                        if (rr < 0 || rr >= H || cc < 0 || cc >= W) continue;
+                        const size_t t = (size_t)rr * W + cc;
+                        if (!seen[t] && disp[t] != invalid_val && fabsf(disp[t] - base) <= diff) { /* :290-292 */
+                            queue[tail++] = (int32_t)t;
+                            seen[t] = 1;
+                        }
+                    }
+            }
+            if (tail < min_area) /* :304 */
+                for (size_t k = 0; k < tail; ++k) disp[queue[k]] = (float)invalid_val;
+        }
+    free(seen);
+    free(queue);
+}
+
+/* The shipped call `RemoveSpeckles(disp, W, H, 1, 30, Invalid_Float)` (main.cpp:93) binds +inf to `const int&`;
+ * g++ folds that conversion to INT_MAX, which is what the compiled reference uses. */
+void orc_remove_speckles_inf(float* disp, int W, int H, int diff, unsigned min_area) {
+    orc_remove_speckles(disp, W, H, diff, min_area, 2147483647);
+}
+
+static int cmp_float(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* MedianFilter (:314-344): in-bounds taps, element [n/2] of the sorted window */
+void orc_median(const float* in, float* out, int W, int H, int k) {
+    const int r = k / 2;
+    float* w = (float*)malloc((size_t)k * k * sizeof(float) + sizeof(float));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            int n = 0;
+            for (int a = -r; a <= r; ++a)
+                for (int b = -r; b <= r; ++b) {
+                    const int y = i + a, x = j + b;
+                    if (y >= 0 && y < H && x >= 0 && x < W) w[n++] = in[(size_t)y * W + x];
+                }
+            qsort(w, (size_t)n, sizeof(float), cmp_float);
+            out[(size_t)i * W + j] = w[n / 2];
+        }
+    free(w);
+}

@@ -23,8 +23,6 @@ void orc_adcensus(const float* left, const float* right, int H, int W, int D, fl
                   int do_right, float* costL, float* costR, float* adL, float* adR, float* censusL, float* censusR,
                   float* wtaL, float* wtaR);
 void orc_wta(const float* vol, int H, int W, int D, float* disp);
-int orc_crossarm(const uint8_t* img, int ch, int H, int W, int D, int tao, int32_t* armL, int32_t* armR,
-                 int32_t* armT, int32_t* armB, int mode, const float* vol_in, float* vol_out);
 void orc_scanline(const float* cost, const float* gray, int H, int W, int D, int p1, int p2, float* left,
                   float* right, float* up, float* down, float* sum, float* disp);
 void orc_lrcheck(float* dispL, const float* dispR, int W, int H, int gate, int32_t* occ, int32_t* n_occ, int32_t* mis,
@@ -37,22 +35,7 @@ void orc_median(const float* in, float* out, int W, int H, int k);
 int orc_cross_aggregate(const uint8_t* bgrL, const uint8_t* bgrR, const float* cost_init, int W, int H, int D, int L1,
                         int L2, int t1, int t2, int iters, float* cost_out, uint8_t* arms, uint16_t* sup0,
                         uint16_t* sup1);
-void orc_cblsm_ad(const uint8_t* left, const uint8_t* right, int H, int W, int D, float* adL, float* adR);
-void orc_cblsm_arms(const uint8_t* img, int ch, int H, int W, int tao, int maxLength, int secLength, int32_t* armL,
-                    int32_t* armR, int32_t* armUp, int32_t* armDown);
-void orc_cblsm_aggregate_v5(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
-                            const int32_t* armUp, const int32_t* armDown, int D, int H, int W);
-void orc_cblsm_wta(const float* vol, float* disp, int D, int H, int W);
-void orc_sad_left(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, int32_t* disp);
-void orc_sad_right(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, int32_t* disp);
-void orc_sad_costs_left(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, float* costs);
-float orc_sad_optimal_disparity(const float* sad, int D);
-void orc_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int D, int32_t* disp);
-double orc_ncc_cost(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int i, int j, int d);
-void orc_asw(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, int D, double spaceSigma,
-             double colorSigma, int T, int right_view, float* disp);
-void orc_asw_masks(int winSize, double spaceSigma, double colorSigma, double* space_out, double* color_out);
-void orc_asw_crosscheck(const float* dispL, const float* dispR, int H, int W, uint8_t* out);
+/* (crossarm / CBLSM / SAD / NCC / ASW restatements are appended below as they are pinned) */
 
 #ifdef __cplusplus
 }

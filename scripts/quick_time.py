@@ -24,7 +24,7 @@ def run(H, W, D, mode, reps=3):
     e.close()
 
 if __name__ == "__main__":
-    modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0]
+    modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1]
     for m in modes:
         run(375, 450, 64, m)
         run(1080, 1920, 256, m, reps=2)

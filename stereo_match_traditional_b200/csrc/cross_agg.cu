@@ -173,6 +173,8 @@ smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const float* 
                 "smt_aggregate_cross: bad argument");
     SMT_REQUIRE(ctx, mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST, SMT_ERR_INVALID_ARG,
                 "smt_aggregate_cross: unknown sum mode");
+    SMT_REQUIRE(ctx, mode != SMT_SUM_FAST || L1 <= 34, SMT_ERR_UNSUPPORTED,
+                "smt_aggregate_cross: SMT_SUM_FAST tiles assume arms <= 34 (cross_L1 <= 34, the reference default)");
     SMT_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t npix = (size_t)rows * cols, nvol = npix * D;
     Marshal ms(ctx, space);

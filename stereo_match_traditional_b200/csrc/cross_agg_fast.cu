@@ -1,6 +1,174 @@
-// placeholder, replaced below
+// SMT_SUM_FAST cross aggregation: shared-memory line kernels.
+//
+// Same passes as CrossAggregator::AggregateInArms (CBLSM/cross_aggregator.cpp:327-394), different evaluation:
+//   * a pass along a line (row for the horizontal arm pair, column for the vertical pair) is a variable-width
+//     window sum  out[i] = sum_{t=-lo(i)..hi(i)} in[i+t]  -> one exclusive prefix E per line, out[i] = E[i+hi+1]-E[i-lo];
+//   * the prefix is kept in float64, so E differences are the exact window sum to ~1e-13 and are rounded to float32
+//     ONCE (the reference rounds after every one of its <=68 sequential adds, so the two differ by the reference's own
+//     rounding noise, ~1e-7..1e-6 relative; tests hold the volume to <=1e-5);
+//   * consecutive passes in the same direction (the reference alternates H,V | V,H | H,V | V,H, so V,V and H,H pairs
+//     occur) are fused in one kernel: 8 passes -> 5 sweeps over the volume.
+// A CTA owns a tile of one line: TL consecutive positions (+34 halo per pass each side) x 32 consecutive disparities.
+// Lane = disparity (every global access is a 128-byte row of the [H][W][D] volume), warp w owns the w-th eighth of the
+// tile positions: it loads them straight into registers (~41-49 independent 128 B loads in flight per warp), the 8
+// warps exchange segment totals through shared memory, then each writes its slice of E.  Queries read two float64 per
+// output from shared memory; arms and support counts are warp-uniform broadcast loads.
 #include "common.cuh"
-smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float*, float*, const uint8_t*, const uint16_t*, const uint16_t*, int, int, int, int,
-                                    float**) {
-    return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "SMT_SUM_FAST not built yet");
+
+namespace {
+
+constexpr int AGG_WARPS = 8;
+constexpr int AGG_THREADS = AGG_WARPS * 32;
+constexpr int ARM_MAX = 34 + 1;  // the kernels assume arms <= 34 (L1 <= 34); checked on the host
+
+template <int NPASS>
+struct AggCfg {
+    static constexpr int HALO = 34 * NPASS;
+    static constexpr int MAXSEG = NPASS == 1 ? 41 : 49;     // positions per warp
+    static constexpr int MAXN = MAXSEG * AGG_WARPS;          // loaded positions per tile (328 / 392)
+    static constexpr int MAXTL = MAXN - 2 * HALO;            // 260 / 256 output positions per tile
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)(MAXN + 1) * 32 + AGG_WARPS * 32);
+};
+
+// horiz: line index = row, position = column;  else line index = column, position = row.
+template <int NPASS>
+__global__ void __launch_bounds__(AGG_THREADS, 2)
+    agg_line_kernel(const float* __restrict__ in, float* __restrict__ out, const uchar4* __restrict__ arms,
+                    const uint16_t* __restrict__ supA, const uint16_t* __restrict__ supB, int H, int W, int D, int horiz,
+                    int TL, int ntile) {
+    using Cfg = AggCfg<NPASS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* E = reinterpret_cast<double*>(smem_raw);          // [(MAXN+1)][32]
+    double* tot = E + (size_t)(Cfg::MAXN + 1) * 32;           // [AGG_WARPS][32]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x % ntile, chunk = blockIdx.x / ntile;
+    const int line = blockIdx.y;
+    const int len = horiz ? W : H;
+    const int d = chunk * 32 + lane;
+    const bool act = d < D;
+    const long long pstride = horiz ? 1 : (long long)W;       // pixel-index step along the line
+    const long long pbase = horiz ? (long long)line * W : (long long)line;
+
+    const int c0 = tile * TL, c1 = min(len, c0 + TL);         // output positions
+    const int l0 = max(0, c0 - Cfg::HALO), l1 = min(len, c1 + Cfg::HALO);  // loaded positions
+    const int nload = l1 - l0;
+    const int seg = (nload + AGG_WARPS - 1) / AGG_WARPS;      // <= MAXSEG
+    const int s0 = warp * seg, s1 = min(nload, s0 + seg);     // my local positions [s0, s1)
+
+    float v[Cfg::MAXSEG];
+#pragma unroll
+    for (int k = 0; k < Cfg::MAXSEG; ++k) {
+        const int j = s0 + k;
+        v[k] = 0.f;
+        if (j < s1 && act) v[k] = __ldg(in + (pbase + pstride * (l0 + j)) * D + d);
+    }
+
+    // valid range of the CURRENT pass's input line, in local coordinates
+    int r0 = 0, r1 = nload;
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        const bool last = pass == NPASS - 1;
+        // ---- exclusive prefix of v over [r0, r1) into E
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < Cfg::MAXSEG; ++k) {
+            const int j = s0 + k;
+            if (j < s1 && j >= r0 && j < r1) t += (double)v[k];
+        }
+        tot[warp * 32 + lane] = t;
+        __syncthreads();
+        double acc = 0.0;
+        for (int w = 0; w < warp; ++w) acc += tot[w * 32 + lane];
+#pragma unroll
+        for (int k = 0; k < Cfg::MAXSEG; ++k) {
+            const int j = s0 + k;
+            if (j < s1 && j >= r0 && j < r1) {
+                E[(size_t)j * 32 + lane] = acc;
+                acc += (double)v[k];
+            }
+        }
+        // the closing element E[r1] comes from the warp that owns position r1-1
+        if (r1 - 1 >= s0 && r1 - 1 < s1) E[(size_t)r1 * 32 + lane] = acc;
+        __syncthreads();
+
+        // ---- window sums for the positions the next stage needs
+        const int q0 = last ? (c0 - l0) : max(r0, c0 - l0 - 34 * (NPASS - 1 - pass));
+        const int q1 = last ? (c1 - l0) : min(r1, c1 - l0 + 34 * (NPASS - 1 - pass));
+        const uint16_t* sup = pass == 0 ? supA : supB;
+#pragma unroll
+        for (int k = 0; k < Cfg::MAXSEG; ++k) {
+            const int j = s0 + k;
+            float r = 0.f;
+            if (j < s1 && j >= q0 && j < q1) {
+                const long long pix = pbase + pstride * (l0 + j);
+                const uchar4 a = __ldg(arms + pix);
+                const int lo = horiz ? a.x : a.z, hi = horiz ? a.y : a.w;
+                const double s = E[(size_t)(j + hi + 1) * 32 + lane] - E[(size_t)(j - lo) * 32 + lane];
+                r = (float)s;
+                if (sup) r = __fdiv_rn(r, (float)(int)__ldg(sup + pix));
+                if (last && act) out[pix * D + d] = r;
+            }
+            v[k] = r;
+        }
+        if (!last) {
+            r0 = q0;
+            r1 = q1;
+            __syncthreads();  // everyone is done reading E before the next pass overwrites it
+        }
+    }
+}
+
+struct Pass {
+    bool horiz;
+    const uint16_t* sup;
+};
+
+}  // namespace
+
+smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float** result) {
+    StageTimer t(ctx, ST_AGGREGATE);
+    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    // pass list (cross_aggregator.cpp:102-117): horizontal-first on even iterations; the second pass divides
+    std::vector<Pass> passes;
+    bool hfirst = true;
+    for (int k = 0; k < iters; ++k) {
+        passes.push_back({hfirst, nullptr});
+        passes.push_back({!hfirst, hfirst ? sup0 : sup1});
+        hfirst = !hfirst;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<1>::SMEM));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<2>::SMEM));
+        attr_set = true;
+    }
+    float* cur = vol;
+    float* oth = tmp;
+    const int nchunk = (D + 31) / 32;
+    for (size_t k = 0; k < passes.size();) {
+        const bool fuse = k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz;
+        const int horiz = passes[k].horiz ? 1 : 0;
+        const int len = horiz ? W : H, nlines = horiz ? H : W;
+        const int maxtl = fuse ? AggCfg<2>::MAXTL : AggCfg<1>::MAXTL;
+        const int ntile = (len + maxtl - 1) / maxtl;
+        const int TL = (len + ntile - 1) / ntile;
+        dim3 grid((unsigned)(ntile * nchunk), (unsigned)nlines);
+        if (nlines > 65535) return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "aggregate: more than 65535 lines per direction");
+        if (fuse) {
+            SMT_LAUNCH(ctx, agg_line_kernel<2>, grid, AGG_THREADS, AggCfg<2>::SMEM, cur, oth, arms, passes[k].sup,
+                       passes[k + 1].sup, H, W, D, horiz, TL, ntile);
+            k += 2;
+        } else {
+            SMT_LAUNCH(ctx, agg_line_kernel<1>, grid, AGG_THREADS, AggCfg<1>::SMEM, cur, oth, arms, passes[k].sup,
+                       (const uint16_t*)nullptr, H, W, D, horiz, TL, ntile);
+            k += 1;
+        }
+        float* sw = cur;
+        cur = oth;
+        oth = sw;
+    }
+    *result = cur;
+    return SMT_OK;
 }

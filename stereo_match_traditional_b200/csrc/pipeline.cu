@@ -38,6 +38,8 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     const int H = p->rows, W = p->cols, D = p->D;
     SMT_REQUIRE(ctx, H > 0 && W > 0 && D > 0 && p->agg_iters >= 0, SMT_ERR_INVALID_ARG,
                 "smt_pipeline_adcensus_full: rows, cols, D must be positive");
+    SMT_REQUIRE(ctx, p->sum_mode != SMT_SUM_FAST || p->L1 <= 34, SMT_ERR_UNSUPPORTED,
+                "smt_pipeline_adcensus_full: SMT_SUM_FAST tiles assume arms <= 34 (L1 <= 34, the reference default)");
     SMT_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t npix = (size_t)H * W, nvol = npix * D;
 

@@ -138,3 +138,46 @@ def test_pipeline_reference_order_bit_exact(engine, oracle, H, W, D, kind, seed)
     # gray computed on the device from BGR (cvtColor fixed-point formula) gives the same answer
     got2 = engine.pipeline(p["bgr_left"], p["bgr_right"], D)
     assert np.array_equal(got2["disp"], ref["disp"])
+
+
+# ---------------------------------------------------------------------------------------------- SMT_SUM_FAST
+FAST_SHAPES = SHAPES[:5] + [(70, 300, 36, "scene", 13), (300, 41, 33, "scene", 14), (12, 700, 8, "scene", 15)]
+
+
+@pytest.mark.parametrize("H,W,D,kind,seed", FAST_SHAPES)
+def test_cross_aggregate_fast_within_tolerance(engine, oracle, H, W, D, kind, seed):
+    """Tolerance from BASELINE.json north_star: cost-volume relative error <= 1e-5 (element-wise, max)."""
+    from stereo_match_traditional_b200.api import SUM_FAST
+
+    p = make_pair(H, W, D, seed, kind)
+    L = p["gray_left"].astype(np.float32)
+    R = p["gray_right"].astype(np.float32)
+    cost = engine.adcensus_cost(L, R, D)["cost"]          # realistic costs incl. exact zeros
+    ref = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], cost)["cost"]
+    for iters in (1, 2, 4):
+        refk = ref if iters == 4 else oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], cost, iters=iters)["cost"]
+        got = engine.aggregate_cross(p["bgr_left"], cost, iters=iters, mode=SUM_FAST)["cost"]
+        err, same = rel_err(got, refk)
+        assert err <= 1e-5, f"iters={iters}: max rel err {err:.3e} ({same:.2%} bit-identical)"
+    # integer-valued input: the first iteration is exact under any summation order (SURVEY.md A5)
+    icost = np.rint(cost * 100).astype(np.float32)
+    r1 = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], icost, iters=1)["cost"]
+    g1 = engine.aggregate_cross(p["bgr_left"], icost, iters=1, mode=SUM_FAST)["cost"]
+    assert np.array_equal(g1, r1)
+
+
+@pytest.mark.parametrize("H,W,D,kind,seed", [(48, 200, 24, "scene", 31), (60, 90, 32, "noise", 32), (120, 300, 40, "scene", 34)])
+def test_pipeline_fast_disparities(engine, oracle, H, W, D, kind, seed):
+    """>= 99.9 % of final disparity pixels identical, the rest within +-1 (north_star)."""
+    from stereo_match_traditional_b200.api import SUM_FAST
+
+    p = make_pair(H, W, D, seed, kind)
+    ref = oracle_pfull(oracle, p, D)
+    got = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"],
+                          want=("disp", "left_raw", "right_raw", "lrc"), sum_mode=SUM_FAST)
+    for n in ("right_raw", "left_raw"):
+        same = (got[n] == ref[n]).mean()
+        assert same >= 0.999, f"{n}: {same:.4%}"
+        assert np.abs(got[n] - ref[n]).max() <= 1, n
+    same = (got["disp"] == ref["disp"]).mean()
+    assert same >= 0.999, f"disp: {same:.4%}"

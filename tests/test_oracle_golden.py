@@ -1,0 +1,47 @@
+"""CPU: the oracle (C port, and the compiled reference when present) against the golden fixtures.
+
+The fixtures are outputs of the compiled, unmodified reference (oracle/make_golden.py); this is what pins the port.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.make_golden import ADCENSUS_CASES, adcensus_path, digest
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+DIGESTS = json.loads((GOLDEN / "digests.json").read_text())
+
+
+@pytest.mark.parametrize("case", ADCENSUS_CASES, ids=[c[0] for c in ADCENSUS_CASES])
+def test_port_reproduces_reference_golden(oracle_port, case):
+    name, H, W, D, kind, seed, full = case
+    out = adcensus_path(oracle_port, H, W, D, kind, seed)
+    want = DIGESTS[name]["outputs"]
+    assert set(out) == set(want)
+    for k, v in out.items():
+        assert digest(v) == want[k], f"{name}:{k}"
+    if full:
+        z = np.load(GOLDEN / f"{name}.npz")
+        for k, v in out.items():
+            assert np.array_equal(v, z[k]), f"{name}:{k}"
+
+
+@pytest.mark.skipif(not orc.have("ref"), reason="compiled reference (oracle/_ref) not present")
+def test_compiled_reference_still_matches_golden():
+    o = orc.Oracle("ref")
+    name, H, W, D, kind, seed, _ = ADCENSUS_CASES[0]
+    out = adcensus_path(o, H, W, D, kind, seed)
+    for k, v in out.items():
+        assert digest(v) == DIGESTS[name]["outputs"][k], k
+
+
+def test_first_min_tie_break_and_constant_image(oracle_port):
+    """All-ties input: first-minimum WTA must return 0 (AD-Census.h:359-372)."""
+    vol = np.ones((4, 5, 9), np.float32)
+    assert np.all(oracle_port.wta(vol) == 0)
+    vol[..., 3] = 0.5
+    vol[..., 6] = 0.5
+    assert np.all(oracle_port.wta(vol) == 3)
