@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the AD-Census full pipeline (P_full) -- BASELINE.json's metric:
+"AD-Census frames/s and Gdisp-evals/s (W*H*D/s) at 1920x1080 D=256".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = one pass of P_full over a batch of `--frames-per-step` distinct synthetic rectified pairs per GPU
+(config 4 of BASELINE.json: batched frame stream, batch-parallel over GPUs, no collective).  Prints ONE JSON line.
+
+  value     frames/s over all ranks, inputs already resident in HBM, CUDA events on the launching stream,
+            barrier + synchronize on both sides, max over ranks
+  e2e       the same metric through the host-memspace C-ABI call (pinned host images in, disparity map out; the
+            H2D / D2H copies are inside the timed region)
+  roofline  dominant stage's kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline / --impl reference
+            the reference's own CPU code (oracle/_ref: the unmodified sources compiled with g++ -O3; falls back to
+            the C port) on a bounded crop of the same workload, one independent frame stream per host core
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+METRIC = "AD-Census frames/s at 1920x1080 D=256 (Gdisp-evals/s = W*H*D*fps/1e9 in `gdisp_evals_per_s`)"
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_worker(rows: int, cols: int, D: int, seed: int, reps: int) -> None:
+    """Child process: P_full with the reference's own code on a crop; prints seconds per repetition."""
+    from oracle import oracle as orc
+    from stereo_match_traditional_b200.synth import make_pair
+
+    kind = "ref" if orc.have("ref") else "port"
+    if kind == "port" and not orc.have("port"):
+        orc.build("port")
+    o = orc.Oracle(kind)
+    p = make_pair(rows, cols, D, seed, "scene")
+    L = p["gray_left"].astype(np.float32)
+    R = p["gray_right"].astype(np.float32)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        c = o.adcensus(L, R, D, want=("costL", "costR"))
+        aggL = o.cross_aggregate(p["bgr_left"], p["bgr_right"], c["costL"])["cost"]
+        aggR = o.cross_aggregate(p["bgr_right"], p["bgr_left"], c["costR"])["cost"]
+        sl = o.scanline(aggL, L, 10, 150, want=("disp",))["disp"]
+        lrc, _, _ = o.lrcheck(sl, o.wta(aggR), 2)
+        o.median(o.remove_speckles(lrc, 1, 30, None), 3)
+        times.append(time.perf_counter() - t0)
+    print(json.dumps({"kind": "reference" if kind == "ref" else "port", "times": times}))
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_streams(rows: int, cols: int, D: int, reps: int, workers: int):
+    """`workers` independent frame streams (one process each).  Returns (kind, wall seconds per step list)."""
+    procs = []
+    for w in range(workers):
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--_cpu_worker", f"{rows},{cols},{D},{2004 + w},{reps}"]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True, cwd=str(ROOT)))
+    outs = []
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("cpu worker failed")
+        outs.append(json.loads(out.strip().splitlines()[-1]))
+    kind = outs[0]["kind"]
+    # step r finishes when the slowest stream finishes repetition r
+    per_step = [max(o["times"][r] for o in outs) for r in range(reps)]
+    return kind, per_step
+
+
+def cpu_sample_shape(H, W, D, budget_s: float):
+    """A crop of the workload whose reference run takes about budget_s seconds on one core (~1.8 Mcell/s measured on the GPU box)."""
+    cols = min(W, 384)
+    cells = 1.8e6 * budget_s
+    rows = int(max(8, min(H, cells / (cols * D))))
+    return rows, cols
+
+
+def reference_arm(args, H, W, D):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = min(host_cores(), 32)
+    budget = max(1.0, 150.0 / (args.steps + args.warmup))
+    rows, cols = cpu_sample_shape(H, W, D, budget)
+    kind, per_step = run_cpu_streams(rows, cols, D, args.steps + args.warmup, workers)
+    timed = per_step[args.warmup:]
+    total = sum(timed)
+    frac = (rows * cols) / float(H * W)  # fraction of a full frame each sample is
+    fps = workers * frac * len(timed) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gdisp_evals_per_s": fps * H * W * D / 1e9,
+        "config": {"workload": f"AD-Census P_full {W}x{H} D={D} (BASELINE.json configs[3]); CPU arm runs a {cols}x{rows} crop "
+                               f"per step per core and scales by area"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": kind,
+                         "sample": f"{cols}x{rows} crop, D={D}, full P_full (both views), {workers} independent streams; "
+                                   "the reference's AD-Census path is single-threaded, so cores are used one stream each"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def measured_hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gpu_arm(args, H, W, D):
+    import torch
+    import torch.distributed as dist
+
+    from stereo_match_traditional_b200.api import SUM_FAST, SUM_REFERENCE_ORDER, Engine
+    from stereo_match_traditional_b200.synth import make_pair
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.frames_per_step
+    mode = SUM_FAST if args.sum_mode == "fast" else SUM_REFERENCE_ORDER
+
+    # distinct frames per rank and per slot (seed 1004 + frame)
+    frames = [make_pair(H, W, D, 1004 + rank * B + f, "scene", frame=rank * B + f) for f in range(B)]
+    keys = ("bgr_left", "bgr_right", "gray_left", "gray_right")
+    dev_frames = [{k: torch.as_tensor(fr[k], device=dev) for k in keys} for fr in frames]
+    pin_frames = [{k: torch.as_tensor(fr[k]).pin_memory() for k in keys} for fr in frames]
+    pin_out = [torch.empty((H, W), dtype=torch.float32).pin_memory() for _ in range(B)]
+    h2d = sum(int(t.numel()) * t.element_size() for t in pin_frames[0].values()) * B
+    d2h = H * W * 4 * B
+
+    stream = torch.cuda.Stream(device=dev)
+    eng = Engine(local, stream.cuda_stream)
+    params = eng.default_params(H, W, D)
+    params.sum_mode = mode
+
+    def step_device():
+        for fr in dev_frames:
+            eng.pipeline(fr["bgr_left"], fr["bgr_right"], D, fr["gray_left"], fr["gray_right"], params=params)
+
+    def step_host():
+        outs = []
+        for fr in pin_frames:
+            outs.append(eng.pipeline(fr["bgr_left"].numpy(), fr["bgr_right"].numpy(), D, fr["gray_left"].numpy(),
+                                     fr["gray_right"].numpy(), params=params)["disp"])
+        return outs
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    eng.sync()
+    l0 = eng.kernel_launches
+    with ClockSampler(local) as clk:
+        ms = timed(step_device, args.steps)
+    launches = eng.kernel_launches - l0
+    fps = world * B * args.steps / (ms / 1e3)
+
+    # end-to-end through the host-memspace ABI (pinned host buffers, copies inside the timed region)
+    step_host()
+    ms_e2e = timed(step_host, args.steps)
+    fps_e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # per-stage CUDA-event times for the roofline of the dominant kernel
+    eng.stage_timing(True)
+    nst = max(1, min(args.steps, 3))
+    for _ in range(nst):
+        step_device()
+    st = {k: v / (nst * B) for k, v in eng.read_stage_timing().items()}  # ms per frame
+    eng.stage_timing(False)
+    V = 4.0 * H * W * D
+    iters = params.agg_iters
+    alg = {"cost": 2 * V, "aggregate": 2 * V * iters * 2, "scanline": 2 * V, "wta": 1 * V}   # SURVEY.md 8(d), both views
+    kern = {"cost": "adcensus_cost_kernel", "aggregate": "agg_line_kernel" if mode == SUM_FAST else "agg_pass_exact_kernel",
+            "scanline": "scan_path_kernel", "wta": "wta_first_min_kernel"}
+    dom = max(alg, key=lambda k: st.get(k, 0.0))
+    peak, how = measured_hbm_peak()
+    ach = alg[dom] / (st[dom] / 1e3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "roofline_traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(kern[dom])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": kern[dom], "peak_source": how,
+                "algorithmic_bytes_per_frame": alg[dom], "stage_ms_per_frame": st[dom],
+                "all_stages": {k: {"ms_per_frame": st.get(k, 0.0), "algorithmic_GBps": (alg[k] / (st[k] / 1e3) / 1e9) if st.get(k) else None}
+                               for k in alg},
+                "other_stage_ms_per_frame": {k: v for k, v in st.items() if k not in alg}}
+
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "gdisp_evals_per_s": fps * H * W * D / 1e9,
+        "config": {"workload": f"AD-Census P_full {W}x{H} D={D} (BASELINE.json configs[3]): census 9x7 + AD cost, cross aggregation x4 "
+                               f"both views, 4-path scanline, WTA, LR check, speckles, median",
+                   "frames_per_step_per_gpu": B, "sum_mode": args.sum_mode, "parallelism": f"frame-parallel x{world}, no collective",
+                   "l2": "no explicit flush: every frame streams two 2.1 GB cost volumes (>> 126 MB L2) and consecutive frames differ"},
+        "clocks": clk.summary(),
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        workers = min(host_cores(), 32)
+        rows, cols = cpu_sample_shape(H, W, D, 15.0)
+        kind, per_step = run_cpu_streams(rows, cols, D, 1, workers)
+        cpu_fps = workers * (rows * cols) / float(H * W) / per_step[0]
+        line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": workers, "kind": kind,
+                                "sample": f"{cols}x{rows} crop, D={D}, full P_full (both views) once per core, scaled by area; "
+                                          f"{per_step[0]:.1f} s wall"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=2)
+    ap.add_argument("--shape", default="1080x1920x256", help="HxWxD")
+    ap.add_argument("--sum-mode", default="fast", choices=["fast", "reference_order"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--_cpu_worker", default=None, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args._cpu_worker:
+        r, c, d, s, n = (int(x) for x in args._cpu_worker.split(","))
+        cpu_worker(r, c, d, s, n)
+        return
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    H, W, D = (int(x) for x in args.shape.lower().split("x"))
+    if args.impl == "reference":
+        reference_arm(args, H, W, D)
+    else:
+        gpu_arm(args, H, W, D)
+
+
+if __name__ == "__main__":
+    main()

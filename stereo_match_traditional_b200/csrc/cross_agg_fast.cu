@@ -3,9 +3,11 @@
 // Same passes as CrossAggregator::AggregateInArms (CBLSM/cross_aggregator.cpp:327-394), different evaluation:
 //   * a pass along a line (row for the horizontal arm pair, column for the vertical pair) is a variable-width
 //     window sum  out[i] = sum_{t=-lo(i)..hi(i)} in[i+t]  -> one exclusive prefix E per line, out[i] = E[i+hi+1]-E[i-lo];
-//   * the prefix is kept in float64, so E differences are the exact window sum to ~1e-13 and are rounded to float32
-//     ONCE (the reference rounds after every one of its <=68 sequential adds, so the two differ by the reference's own
-//     rounding noise, ~1e-7..1e-6 relative; tests hold the volume to <=1e-5);
+//   * the prefix is kept as an unevaluated float32 pair (hi, lo) ("double-single", error-free TwoSum updates, ~2^-46
+//     relative), so E differences are the window sum to ~1e-11 and are rounded to float32 once (the reference rounds
+//     after every one of its <=68 sequential adds, so the two differ by the reference's own rounding noise,
+//     ~1e-7..1e-6 relative; tests hold the volume to <=1e-5).  float64 was measured first and rejected: on this B200
+//     the FP64 pipe (DADD and F2F.F64) sustained ~1.3 lane-ops/clk/SM, 100 ms per frame at 1080p x 256;
 //   * consecutive passes in the same direction (the reference alternates H,V | V,H | H,V | V,H, so V,V and H,H pairs
 //     occur) are fused in one kernel: 8 passes -> 5 sweeps over the volume.
 // A CTA owns a tile of one line: TL consecutive positions (+34 halo per pass each side) x 32 consecutive disparities.
@@ -17,6 +19,36 @@
 
 namespace {
 
+// ---- double-single arithmetic (no FMA contraction: the library is built with -fmad=false) ----
+struct ds {
+    float hi, lo;
+};
+// (a.hi + a.lo) + b, renormalised
+__device__ __forceinline__ ds ds_add_f(ds a, float b) {
+    const float s = __fadd_rn(a.hi, b);
+    const float bb = __fsub_rn(s, a.hi);
+    const float e = __fadd_rn(__fsub_rn(a.hi, __fsub_rn(s, bb)), __fsub_rn(b, bb));  // TwoSum error term
+    const float l = __fadd_rn(a.lo, e);
+    ds r;
+    r.hi = __fadd_rn(s, l);
+    r.lo = __fsub_rn(l, __fsub_rn(r.hi, s));
+    return r;
+}
+__device__ __forceinline__ ds ds_add(ds a, ds b) {
+    const float s = __fadd_rn(a.hi, b.hi);
+    const float bb = __fsub_rn(s, a.hi);
+    const float e = __fadd_rn(__fsub_rn(a.hi, __fsub_rn(s, bb)), __fsub_rn(b.hi, bb));
+    const float l = __fadd_rn(__fadd_rn(a.lo, b.lo), e);
+    ds r;
+    r.hi = __fadd_rn(s, l);
+    r.lo = __fsub_rn(l, __fsub_rn(r.hi, s));
+    return r;
+}
+// float32(b - a) for prefix values b >= a of one chain
+__device__ __forceinline__ float ds_diff(float2 b, float2 a) {
+    return __fadd_rn(__fsub_rn(b.x, a.x), __fsub_rn(b.y, a.y));
+}
+
 constexpr int AGG_WARPS = 8;
 constexpr int AGG_THREADS = AGG_WARPS * 32;
 constexpr int ARM_MAX = 34 + 1;  // the kernels assume arms <= 34 (L1 <= 34); checked on the host
@@ -27,7 +59,8 @@ struct AggCfg {
     static constexpr int MAXSEG = NPASS == 1 ? 41 : 49;     // positions per warp
     static constexpr int MAXN = MAXSEG * AGG_WARPS;          // loaded positions per tile (328 / 392)
     static constexpr int MAXTL = MAXN - 2 * HALO;            // 260 / 256 output positions per tile
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)(MAXN + 1) * 32 + AGG_WARPS * 32);
+    static constexpr size_t SMEM = sizeof(float2) * ((size_t)(MAXN + 1) * 32 + AGG_WARPS * 32) + sizeof(unsigned) * MAXN +
+                                   sizeof(float) * MAXN * NPASS;
 };
 
 // horiz: line index = row, position = column;  else line index = column, position = row.
@@ -38,8 +71,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2)
                     int TL, int ntile) {
     using Cfg = AggCfg<NPASS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* E = reinterpret_cast<double*>(smem_raw);          // [(MAXN+1)][32]
-    double* tot = E + (size_t)(Cfg::MAXN + 1) * 32;           // [AGG_WARPS][32]
+    float2* E = reinterpret_cast<float2*>(smem_raw);          // [(MAXN+1)][32] (hi, lo)
+    float2* tot = E + (size_t)(Cfg::MAXN + 1) * 32;           // [AGG_WARPS][32]
+    unsigned* win = reinterpret_cast<unsigned*>(tot + AGG_WARPS * 32);   // [MAXN] (j-lo) | (j+hi+1)<<16
+    float* supf = reinterpret_cast<float*>(win + Cfg::MAXN);             // [NPASS][MAXN] divisors as float
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x % ntile, chunk = blockIdx.x / ntile;
@@ -54,68 +89,78 @@ __global__ void __launch_bounds__(AGG_THREADS, 2)
     const int l0 = max(0, c0 - Cfg::HALO), l1 = min(len, c1 + Cfg::HALO);  // loaded positions
     const int nload = l1 - l0;
     const int seg = (nload + AGG_WARPS - 1) / AGG_WARPS;      // <= MAXSEG
-    const int s0 = warp * seg, s1 = min(nload, s0 + seg);     // my local positions [s0, s1)
+    const int s0 = min(nload, warp * seg), s1 = min(nload, s0 + seg);     // my local positions [s0, s1)
+    const int nseg = s1 - s0;
 
+    // ---- my segment of the input line, straight into registers (independent 128-byte row loads)
     float v[Cfg::MAXSEG];
+    {
+        const float* src = in + (pbase + pstride * (l0 + s0)) * D + d;
+        const long long step = pstride * D;
 #pragma unroll
-    for (int k = 0; k < Cfg::MAXSEG; ++k) {
-        const int j = s0 + k;
-        v[k] = 0.f;
-        if (j < s1 && act) v[k] = __ldg(in + (pbase + pstride * (l0 + j)) * D + d);
+        for (int k = 0; k < Cfg::MAXSEG; ++k) {
+            v[k] = 0.f;
+            if (k < nseg && act) v[k] = __ldg(src + step * k);
+        }
+    }
+    // ---- window descriptors and divisors of the tile (warp-uniform in the query loops)
+    for (int j = threadIdx.x; j < nload; j += AGG_THREADS) {
+        const long long pix = pbase + pstride * (l0 + j);
+        const uchar4 a = __ldg(arms + pix);
+        const int lo = horiz ? a.x : a.z, hi = horiz ? a.y : a.w;
+        // clamp to the loaded range: only halo positions whose result is never used can exceed it
+        win[j] = (unsigned)max(j - lo, 0) | ((unsigned)min(j + hi + 1, nload) << 16);
+        if (supA) supf[j] = (float)(int)__ldg(supA + pix);
+        if (NPASS == 2 && supB) supf[Cfg::MAXN + j] = (float)(int)__ldg(supB + pix);
     }
 
-    // valid range of the CURRENT pass's input line, in local coordinates
-    int r0 = 0, r1 = nload;
 #pragma unroll
     for (int pass = 0; pass < NPASS; ++pass) {
         const bool last = pass == NPASS - 1;
-        // ---- exclusive prefix of v over [r0, r1) into E
-        double t = 0.0;
+        // ---- exclusive double-single prefix of the line into E (positions outside the valid range hold 0)
+        ds t = {0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < Cfg::MAXSEG; ++k) {
-            const int j = s0 + k;
-            if (j < s1 && j >= r0 && j < r1) t += (double)v[k];
-        }
-        tot[warp * 32 + lane] = t;
+        for (int k = 0; k < Cfg::MAXSEG; ++k) t = ds_add_f(t, v[k]);
+        tot[warp * 32 + lane] = make_float2(t.hi, t.lo);
         __syncthreads();
-        double acc = 0.0;
-        for (int w = 0; w < warp; ++w) acc += tot[w * 32 + lane];
-#pragma unroll
-        for (int k = 0; k < Cfg::MAXSEG; ++k) {
-            const int j = s0 + k;
-            if (j < s1 && j >= r0 && j < r1) {
-                E[(size_t)j * 32 + lane] = acc;
-                acc += (double)v[k];
-            }
+        ds acc = {0.f, 0.f};
+        for (int w = 0; w < warp; ++w) {
+            const float2 tw = tot[w * 32 + lane];
+            acc = ds_add(acc, ds{tw.x, tw.y});
         }
-        // the closing element E[r1] comes from the warp that owns position r1-1
-        if (r1 - 1 >= s0 && r1 - 1 < s1) E[(size_t)r1 * 32 + lane] = acc;
+        {
+            float2* e = E + (size_t)s0 * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < Cfg::MAXSEG; ++k) {
+                if (k < nseg) e[k * 32] = make_float2(acc.hi, acc.lo);
+                acc = ds_add_f(acc, v[k]);
+            }
+            if (warp == AGG_WARPS - 1) E[(size_t)nload * 32 + lane] = make_float2(acc.hi, acc.lo);
+        }
         __syncthreads();
 
-        // ---- window sums for the positions the next stage needs
-        const int q0 = last ? (c0 - l0) : max(r0, c0 - l0 - 34 * (NPASS - 1 - pass));
-        const int q1 = last ? (c1 - l0) : min(r1, c1 - l0 + 34 * (NPASS - 1 - pass));
-        const uint16_t* sup = pass == 0 ? supA : supB;
+        // ---- window sums for the positions the next stage needs (local range [q0, q1))
+        const int q0 = last ? (c0 - l0) : max(0, c0 - l0 - 34 * (NPASS - 1 - pass));
+        const int q1 = last ? (c1 - l0) : min(nload, c1 - l0 + 34 * (NPASS - 1 - pass));
+        const bool has_sup = (pass == 0 ? supA : supB) != nullptr;
+        const float* sf = supf + pass * Cfg::MAXN + s0;
+        const unsigned* wn = win + s0;
+        const float2* El = E + lane;
+        float* dst = out + (pbase + pstride * (l0 + s0)) * D + d;
+        const long long step = pstride * D;
+        const int k0 = q0 - s0, k1 = min(q1 - s0, nseg);
 #pragma unroll
         for (int k = 0; k < Cfg::MAXSEG; ++k) {
-            const int j = s0 + k;
             float r = 0.f;
-            if (j < s1 && j >= q0 && j < q1) {
-                const long long pix = pbase + pstride * (l0 + j);
-                const uchar4 a = __ldg(arms + pix);
-                const int lo = horiz ? a.x : a.z, hi = horiz ? a.y : a.w;
-                const double s = E[(size_t)(j + hi + 1) * 32 + lane] - E[(size_t)(j - lo) * 32 + lane];
-                r = (float)s;
-                if (sup) r = __fdiv_rn(r, (float)(int)__ldg(sup + pix));
-                if (last && act) out[pix * D + d] = r;
+            if (k >= k0 && k < k1) {
+                const unsigned w = wn[k];
+                r = ds_diff(El[(w >> 16) * 32], El[(w & 0xffffu) * 32]);
+                if (has_sup) r = __fdiv_rn(r, sf[k]);
+                if (last && act) dst[step * k] = r;
             }
             v[k] = r;
         }
-        if (!last) {
-            r0 = q0;
-            r1 = q1;
-            __syncthreads();  // everyone is done reading E before the next pass overwrites it
-        }
+        if (!last) __syncthreads();  // everyone is done reading E before the next pass overwrites it
     }
 }
 

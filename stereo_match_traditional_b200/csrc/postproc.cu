@@ -204,29 +204,67 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     } while (!done);
 }
 
-__global__ void __launch_bounds__(256) spk_init_kernel(const float* __restrict__ disp, size_t n, float invalid, int* __restrict__ label,
-                                                       int* __restrict__ size) {
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    label[p] = (disp[p] == invalid) ? -1 : (int)p;  // :262 float == (float)int
-    size[p] = 0;
+// edge predicate of the reference's region growing (:290-292): both valid, |delta| <= diff
+__device__ __forceinline__ bool spk_conn(float a, float b, float invalid, float diff) {
+    return a != invalid && b != invalid && fabsf(a - b) <= diff;
 }
-__global__ void __launch_bounds__(256) spk_merge_kernel(const float* __restrict__ disp, int W, int H, float diff, int* __restrict__ label) {
+
+// Stage 1: one block per row.  label = start index of the pixel's horizontal run (pointer jumping in shared
+// memory, log2(W) rounds), -1 for invalid pixels.  Rows are the long direction, so this removes the long chains a
+// naive per-pixel union-find would have to walk.
+__global__ void __launch_bounds__(256) spk_rows_kernel(const float* __restrict__ disp, int W, float invalid, float diff,
+                                                       int* __restrict__ label, int* __restrict__ size) {
+    extern __shared__ int s_l[];  // W ints
+    const int i = blockIdx.x;
+    const float* row = disp + (size_t)i * W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        const float v = row[j];
+        int l = j;
+        if (v == invalid) l = -1;  // :262 (float == (float)int)
+        else if (j > 0 && spk_conn(v, row[j - 1], invalid, diff)) l = j - 1;
+        s_l[j] = l;
+        size[(size_t)i * W + j] = 0;
+    }
+    __syncthreads();
+    for (int span = 1; span < W; span <<= 1) {
+        // monotone pointer jumping: reading a value another thread is updating only ever yields an ancestor
+        for (int j = threadIdx.x; j < W; j += blockDim.x) {
+            const int l = ((volatile int*)s_l)[j];
+            if (l >= 0) {
+                const int ll = ((volatile int*)s_l)[l];
+                if (ll != l) ((volatile int*)s_l)[j] = ll;
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        const int l = s_l[j];
+        label[(size_t)i * W + j] = l < 0 ? -1 : i * W + l;
+    }
+}
+
+// Stage 2: link runs of adjacent rows.  A (pixel, neighbour-below) edge is skipped when edges further to the left
+// already imply it (first-contact rule), so large regions issue a handful of unions instead of three per pixel.
+__global__ void __launch_bounds__(256) spk_merge_kernel(const float* __restrict__ disp, int W, int H, float invalid, float diff,
+                                                        int* __restrict__ label) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (size_t)W * H) return;
-    if (label[p] < 0) return;
     const int i = (int)(p / W), j = (int)(p - (size_t)i * W);
+    if (i + 1 >= H) return;
     const float v = disp[p];
-    // forward half of the 8-neighbourhood: E, SW, S, SE
-    const int dr[4] = {0, 1, 1, 1}, dc[4] = {1, -1, 0, 1};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = i + dr[k], c = j + dc[k];
-        if (r < 0 || r >= H || c < 0 || c >= W) continue;
-        const size_t q = (size_t)r * W + c;
-        if (((volatile int*)label)[q] < 0) continue;
-        if (fabsf(disp[q] - v) <= diff) uf_union(label, (int)p, (int)q);  // :292 (NaN compares false, as in the reference)
-    }
+    if (v == invalid) return;
+    const float* r0 = disp + (size_t)i * W;
+    const float* r1 = r0 + W;
+    const float vl = j > 0 ? r0[j - 1] : invalid, vr = j + 1 < W ? r0[j + 1] : invalid;
+    const float sw = j > 0 ? r1[j - 1] : invalid, ss = r1[j], se = j + 1 < W ? r1[j + 1] : invalid;
+    const bool c_l = spk_conn(v, vl, invalid, diff), c_r = spk_conn(v, vr, invalid, diff);
+    const bool c_s = spk_conn(v, ss, invalid, diff), c_sw = spk_conn(v, sw, invalid, diff), c_se = spk_conn(v, se, invalid, diff);
+    const size_t q = p + W;
+    if (c_s && !(c_l && spk_conn(ss, sw, invalid, diff) && spk_conn(vl, sw, invalid, diff))) uf_union(label, (int)p, (int)q);
+    if (c_sw && !(c_l && spk_conn(vl, sw, invalid, diff)) && !(c_s && spk_conn(ss, sw, invalid, diff)))
+        uf_union(label, (int)p, (int)(q - 1));
+    if (c_se && !(c_s && spk_conn(ss, se, invalid, diff)) && !(c_r && spk_conn(vr, se, invalid, diff)))
+        uf_union(label, (int)p, (int)(q + 1));
 }
 __global__ void __launch_bounds__(256) spk_count_kernel(int* __restrict__ label, size_t n, int* __restrict__ size) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,8 +290,11 @@ smt_status_t k_remove_speckles(smt_ctx* ctx, float* disp, int W, int H, int diff
     SMT_ALLOC(ctx, label, n * sizeof(int));
     SMT_ALLOC(ctx, size, n * sizeof(int));
     const float inv = (float)invalid_val;
-    SMT_LAUNCH(ctx, spk_init_kernel, nb, 256, 0, disp, n, inv, label.as<int>(), size.as<int>());
-    SMT_LAUNCH(ctx, spk_merge_kernel, nb, 256, 0, disp, W, H, (float)diff, label.as<int>());
+    if ((size_t)W * sizeof(int) > 200 * 1024) return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "remove_speckles: width %d too large", W);
+    if ((size_t)W * sizeof(int) > 48 * 1024)
+        SMT_CUDA(ctx, cudaFuncSetAttribute(spk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W * sizeof(int))));
+    SMT_LAUNCH(ctx, spk_rows_kernel, H, 256, (size_t)W * sizeof(int), disp, W, inv, (float)diff, label.as<int>(), size.as<int>());
+    SMT_LAUNCH(ctx, spk_merge_kernel, nb, 256, 0, disp, W, H, inv, (float)diff, label.as<int>());
     SMT_LAUNCH(ctx, spk_count_kernel, nb, 256, 0, label.as<int>(), n, size.as<int>());
     SMT_LAUNCH(ctx, spk_apply_kernel, nb, 256, 0, label.as<int>(), size.as<int>(), n, min_area, inv, disp);
     return SMT_OK;
