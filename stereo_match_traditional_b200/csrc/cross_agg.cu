@@ -117,11 +117,11 @@ __global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------- fast line passes
 // (implemented in cross_agg_fast.cu)
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
-                                    const uint16_t* sup1, int H, int W, int D, int iters, float** result);
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result);
 
 smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
-                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float** result) {
-    if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, result);
+                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result) {
+    if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, vmax, result);
     StageTimer t(ctx, ST_AGGREGATE);
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     const size_t ncell = (size_t)H * W * D;
@@ -140,6 +140,45 @@ smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8
         hfirst = !hfirst;
     }
     *result = cur;  // every iteration ends back in `vol`
+    return SMT_OK;
+}
+
+// min / max of a volume (order-preserving uint keys + atomics); used to pick the compensated-prefix variant
+__device__ __forceinline__ unsigned fkey(float f) {
+    unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ v, size_t n, unsigned* __restrict__ out) {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const float x = v[k];
+        const unsigned key = (x == x) ? fkey(x) : 0xffffffffu;  // NaN poisons the max
+        lo = min(lo, key);
+        hi = max(hi, key);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+static smt_status_t volume_nonneg_max(smt_ctx* ctx, const float* vol, size_t n, float* vmax) {
+    SMT_ALLOC(ctx, mm, 2 * sizeof(unsigned));
+    const unsigned init[2] = {0xffffffffu, 0u};
+    SMT_CUDA(ctx, cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    SMT_LAUNCH(ctx, minmax_kernel, ctx->sm_count * 8, 256, 0, vol, n, mm.as<unsigned>());
+    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, mm.p, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned klo = (unsigned)ctx->h_pinned[0], khi = (unsigned)ctx->h_pinned[1];
+    auto unkey = [](unsigned k) {
+        unsigned u = k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu);
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    const float lo = unkey(klo), hi = unkey(khi);
+    *vmax = (khi != 0xffffffffu && lo >= 0.f && hi < 1e30f) ? (hi > 0.f ? hi : 1.f) : -1.f;
     return SMT_OK;
 }
 
@@ -195,7 +234,9 @@ smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const float* 
     if (dout != dinit)
         SMT_CUDA(ctx, cudaMemcpyAsync(dout, dinit, nvol * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     float* res = nullptr;
-    SMT_TRY(k_aggregate_cross(ctx, dout, tmp.as<float>(), darms, ds0, ds1, rows, cols, D, iters, mode, &res));
+    float vmax = -1.f;
+    if (mode == SMT_SUM_FAST) SMT_TRY(volume_nonneg_max(ctx, dout, nvol, &vmax));
+    SMT_TRY(k_aggregate_cross(ctx, dout, tmp.as<float>(), darms, ds0, ds1, rows, cols, D, iters, mode, vmax, &res));
     if (res != dout)
         SMT_CUDA(ctx, cudaMemcpyAsync(dout, res, nvol * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     return ms.finish();

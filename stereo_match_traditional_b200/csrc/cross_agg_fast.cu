@@ -15,6 +15,8 @@
 // tile positions: it loads them straight into registers (~41-49 independent 128 B loads in flight per warp), the 8
 // warps exchange segment totals through shared memory, then each writes its slice of E.  Queries read two float64 per
 // output from shared memory; arms and support counts are warp-uniform broadcast loads.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -59,21 +61,43 @@ struct AggCfg {
     static constexpr int MAXSEG = NPASS == 1 ? 41 : 49;     // positions per warp
     static constexpr int MAXN = MAXSEG * AGG_WARPS;          // loaded positions per tile (328 / 392)
     static constexpr int MAXTL = MAXN - 2 * HALO;            // 260 / 256 output positions per tile
-    static constexpr size_t SMEM = sizeof(float2) * ((size_t)(MAXN + 1) * 32 + AGG_WARPS * 32) + sizeof(unsigned) * MAXN +
+    static constexpr size_t SMEM = sizeof(float2) * ((size_t)(MAXN + 1) * 32 + AGG_WARPS * 32) + sizeof(uint2) * MAXN +
                                    sizeof(float) * MAXN * NPASS;
 };
 
+// ---- cascaded compensated prefix for NON-NEGATIVE inputs (Ogita-Rump-Oishi "Sum2" as a running pair) ---------------
+// state (s, c) represents s + c: s is the plain float32 running sum, c the running sum of the EXACT rounding errors of
+// every s update.  Starting s at a power-of-two bias >= every input keeps |s| >= |v|, so the 3-op FastTwoSum error
+// term is exact; c only ever adds numbers of size ~ulp(s), so its own rounding is second order (2^-48 relative to s).
+// Two chains over the same data (segment totals vs. segment prefixes) therefore agree to second order, which is what
+// lets a window that spans two warps' segments come out exact (e.g. exactly 0 over a run of zero costs).
+// 4 FADD per element instead of 10 for the general TwoSum form above.
+struct ks {
+    float s, c;
+};
+__device__ __forceinline__ ks ks_add(ks a, float v) {
+    ks r;
+    r.s = __fadd_rn(a.s, v);
+    r.c = __fadd_rn(a.c, __fsub_rn(v, __fsub_rn(r.s, a.s)));
+    return r;
+}
+// float32(P_b - P_a), P = s + c
+__device__ __forceinline__ float ks_diff(float2 b, float2 a) {
+    return __fadd_rn(__fsub_rn(b.x, a.x), __fsub_rn(b.y, a.y));
+}
+
 // horiz: line index = row, position = column;  else line index = column, position = row.
-template <int NPASS>
+// NONNEG: inputs are known to be >= 0 and <= the pass's bias: cascaded compensated prefix.
+template <int NPASS, bool NONNEG>
 __global__ void __launch_bounds__(AGG_THREADS, 2)
     agg_line_kernel(const float* __restrict__ in, float* __restrict__ out, const uchar4* __restrict__ arms,
                     const uint16_t* __restrict__ supA, const uint16_t* __restrict__ supB, int H, int W, int D, int horiz,
-                    int TL, int ntile) {
+                    int TL, int ntile, float bias0, float bias1) {
     using Cfg = AggCfg<NPASS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* E = reinterpret_cast<float2*>(smem_raw);          // [(MAXN+1)][32] (hi, lo)
+    float2* E = reinterpret_cast<float2*>(smem_raw);          // [(MAXN+1)][32] prefix pairs
     float2* tot = E + (size_t)(Cfg::MAXN + 1) * 32;           // [AGG_WARPS][32]
-    unsigned* win = reinterpret_cast<unsigned*>(tot + AGG_WARPS * 32);   // [MAXN] (j-lo) | (j+hi+1)<<16
+    uint2* win = reinterpret_cast<uint2*>(tot + AGG_WARPS * 32);         // [MAXN] byte offsets of E[j-lo], E[j+hi+1]
     float* supf = reinterpret_cast<float*>(win + Cfg::MAXN);             // [NPASS][MAXN] divisors as float
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,7 +133,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2)
         const uchar4 a = __ldg(arms + pix);
         const int lo = horiz ? a.x : a.z, hi = horiz ? a.y : a.w;
         // clamp to the loaded range: only halo positions whose result is never used can exceed it
-        win[j] = (unsigned)max(j - lo, 0) | ((unsigned)min(j + hi + 1, nload) << 16);
+        win[j] = make_uint2((unsigned)max(j - lo, 0) * 256u, (unsigned)min(j + hi + 1, nload) * 256u);
         if (supA) supf[j] = (float)(int)__ldg(supA + pix);
         if (NPASS == 2 && supB) supf[Cfg::MAXN + j] = (float)(int)__ldg(supB + pix);
     }
@@ -117,18 +141,42 @@ __global__ void __launch_bounds__(AGG_THREADS, 2)
 #pragma unroll
     for (int pass = 0; pass < NPASS; ++pass) {
         const bool last = pass == NPASS - 1;
-        // ---- exclusive double-single prefix of the line into E (positions outside the valid range hold 0)
-        ds t = {0.f, 0.f};
+        const float bias = pass == 0 ? bias0 : bias1;
+        // ---- exclusive compensated prefix of the line into E (positions outside the valid range hold 0)
+        if (NONNEG) {
+            ks t = {bias, 0.f};
 #pragma unroll
-        for (int k = 0; k < Cfg::MAXSEG; ++k) t = ds_add_f(t, v[k]);
-        tot[warp * 32 + lane] = make_float2(t.hi, t.lo);
-        __syncthreads();
-        ds acc = {0.f, 0.f};
-        for (int w = 0; w < warp; ++w) {
-            const float2 tw = tot[w * 32 + lane];
-            acc = ds_add(acc, ds{tw.x, tw.y});
-        }
-        {
+            for (int k = 0; k < Cfg::MAXSEG; ++k) t = ks_add(t, v[k]);
+            tot[warp * 32 + lane] = make_float2(__fsub_rn(t.s, bias), t.c);  // exact: t.s >= bias, same binade or above
+            __syncthreads();
+            ks acc = {bias, 0.f};
+            for (int w = 0; w < warp; ++w) {
+                const float2 tw = tot[w * 32 + lane];
+                // general TwoSum here: a segment total may exceed the running value (<= 7 steps per thread)
+                const float sn = __fadd_rn(acc.s, tw.x);
+                const float bb = __fsub_rn(sn, acc.s);
+                const float er = __fadd_rn(__fsub_rn(acc.s, __fsub_rn(sn, bb)), __fsub_rn(tw.x, bb));
+                acc.c = __fadd_rn(__fadd_rn(acc.c, tw.y), er);
+                acc.s = sn;
+            }
+            float2* e = E + (size_t)s0 * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < Cfg::MAXSEG; ++k) {
+                if (k < nseg) e[k * 32] = make_float2(acc.s, acc.c);
+                acc = ks_add(acc, v[k]);
+            }
+            if (warp == AGG_WARPS - 1) E[(size_t)nload * 32 + lane] = make_float2(acc.s, acc.c);
+        } else {
+            ds t = {0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < Cfg::MAXSEG; ++k) t = ds_add_f(t, v[k]);
+            tot[warp * 32 + lane] = make_float2(t.hi, t.lo);
+            __syncthreads();
+            ds acc = {0.f, 0.f};
+            for (int w = 0; w < warp; ++w) {
+                const float2 tw = tot[w * 32 + lane];
+                acc = ds_add(acc, ds{tw.x, tw.y});
+            }
             float2* e = E + (size_t)s0 * 32 + lane;
 #pragma unroll
             for (int k = 0; k < Cfg::MAXSEG; ++k) {
@@ -144,8 +192,8 @@ __global__ void __launch_bounds__(AGG_THREADS, 2)
         const int q1 = last ? (c1 - l0) : min(nload, c1 - l0 + 34 * (NPASS - 1 - pass));
         const bool has_sup = (pass == 0 ? supA : supB) != nullptr;
         const float* sf = supf + pass * Cfg::MAXN + s0;
-        const unsigned* wn = win + s0;
-        const float2* El = E + lane;
+        const uint2* wn = win + s0;
+        const unsigned char* El = reinterpret_cast<const unsigned char*>(E + lane);
         float* dst = out + (pbase + pstride * (l0 + s0)) * D + d;
         const long long step = pstride * D;
         const int k0 = q0 - s0, k1 = min(q1 - s0, nseg);
@@ -153,8 +201,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2)
         for (int k = 0; k < Cfg::MAXSEG; ++k) {
             float r = 0.f;
             if (k >= k0 && k < k1) {
-                const unsigned w = wn[k];
-                r = ds_diff(El[(w >> 16) * 32], El[(w & 0xffffu) * 32]);
+                const uint2 w = wn[k];
+                const float2 ea = *reinterpret_cast<const float2*>(El + w.x);
+                const float2 eb = *reinterpret_cast<const float2*>(El + w.y);
+                r = NONNEG ? ks_diff(eb, ea) : ds_diff(eb, ea);
                 if (has_sup) r = __fdiv_rn(r, sf[k]);
                 if (last && act) dst[step * k] = r;
             }
@@ -171,8 +221,9 @@ struct Pass {
 
 }  // namespace
 
+// vmax: an upper bound of the (non-negative) input values, or <= 0 when the sign/range of the input is unknown.
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
-                                    const uint16_t* sup1, int H, int W, int D, int iters, float** result) {
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result) {
     StageTimer t(ctx, ST_AGGREGATE);
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     // pass list (cross_aggregator.cpp:102-117): horizontal-first on even iterations; the second pass divides
@@ -185,15 +236,25 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
     }
     static bool attr_set = false;
     if (!attr_set) {
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<1>::SMEM));
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<2>::SMEM));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<1>::SMEM));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<2>::SMEM));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<1>::SMEM));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<2>::SMEM));
         attr_set = true;
     }
     float* cur = vol;
     float* oth = tmp;
     const int nchunk = (D + 31) / 32;
+    const bool nonneg = vmax > 0.f && vmax < 1e30f;
+    float b_plain = 1.f;  // power of two >= vmax: bias of a pass whose input is a cost (or an average of costs)
+    while (nonneg && b_plain < vmax) b_plain *= 2.f;
+    const float b_sum = b_plain * 128.f;  // input of a dividing pass: sums of <= 69 such values
+    static const bool fuse_pairs = getenv("SMT_AGG_NO_FUSE") == nullptr;
     for (size_t k = 0; k < passes.size();) {
-        const bool fuse = k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz;
+        const bool fuse = fuse_pairs && k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz;
+        // input of pass k is a plain cost if pass k does not divide (it is the first pass of its iteration)
+        const float bias0 = passes[k].sup ? b_sum : b_plain;
+        const float bias1 = fuse ? (passes[k + 1].sup ? b_sum : b_plain) : 0.f;
         const int horiz = passes[k].horiz ? 1 : 0;
         const int len = horiz ? W : H, nlines = horiz ? H : W;
         const int maxtl = fuse ? AggCfg<2>::MAXTL : AggCfg<1>::MAXTL;
@@ -202,12 +263,20 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
         dim3 grid((unsigned)(ntile * nchunk), (unsigned)nlines);
         if (nlines > 65535) return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "aggregate: more than 65535 lines per direction");
         if (fuse) {
-            SMT_LAUNCH(ctx, agg_line_kernel<2>, grid, AGG_THREADS, AggCfg<2>::SMEM, cur, oth, arms, passes[k].sup,
-                       passes[k + 1].sup, H, W, D, horiz, TL, ntile);
+            if (nonneg)
+                SMT_LAUNCH(ctx, (agg_line_kernel<2, true>), grid, AGG_THREADS, AggCfg<2>::SMEM, cur, oth, arms, passes[k].sup,
+                           passes[k + 1].sup, H, W, D, horiz, TL, ntile, bias0, bias1);
+            else
+                SMT_LAUNCH(ctx, (agg_line_kernel<2, false>), grid, AGG_THREADS, AggCfg<2>::SMEM, cur, oth, arms, passes[k].sup,
+                           passes[k + 1].sup, H, W, D, horiz, TL, ntile, bias0, bias1);
             k += 2;
         } else {
-            SMT_LAUNCH(ctx, agg_line_kernel<1>, grid, AGG_THREADS, AggCfg<1>::SMEM, cur, oth, arms, passes[k].sup,
-                       (const uint16_t*)nullptr, H, W, D, horiz, TL, ntile);
+            if (nonneg)
+                SMT_LAUNCH(ctx, (agg_line_kernel<1, true>), grid, AGG_THREADS, AggCfg<1>::SMEM, cur, oth, arms, passes[k].sup,
+                           (const uint16_t*)nullptr, H, W, D, horiz, TL, ntile, bias0, bias1);
+            else
+                SMT_LAUNCH(ctx, (agg_line_kernel<1, false>), grid, AGG_THREADS, AggCfg<1>::SMEM, cur, oth, arms, passes[k].sup,
+                           (const uint16_t*)nullptr, H, W, D, horiz, TL, ntile, bias0, bias1);
             k += 1;
         }
         float* sw = cur;

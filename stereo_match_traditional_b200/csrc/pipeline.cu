@@ -101,12 +101,12 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     // ---- right view: cost -> aggregate -> WTA
     float* res = nullptr;
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 1, volA.as<float>(), nullptr, nullptr));
-    SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode, &res));
+    SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode, 2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res));
     SMT_TRY(k_wta(ctx, res, H, W, D, dispR.as<float>()));
 
     // ---- left view: cost -> aggregate -> 4-path scanline with fused WTA
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 0, volA.as<float>(), nullptr, nullptr));
-    SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aL, s0L, s1L, H, W, D, p->agg_iters, p->sum_mode, &res));
+    SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aL, s0L, s1L, H, W, D, p->agg_iters, p->sum_mode, 2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res));
     float* scratch = (res == volA.as<float>()) ? volB.as<float>() : volA.as<float>();
     SMT_TRY(k_scanline(ctx, res, grayf.as<float>(), H, W, D, p->p1, p->p2, nullptr, nullptr, nullptr, nullptr, nullptr,
                        dispL.as<float>(), scratch, nullptr));

@@ -268,11 +268,14 @@ __global__ void __launch_bounds__(256) spk_merge_kernel(const float* __restrict_
 }
 __global__ void __launch_bounds__(256) spk_count_kernel(int* __restrict__ label, size_t n, int* __restrict__ size) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    if (label[p] < 0) return;
-    const int root = uf_find(label, (int)p);
-    label[p] = root;  // roots keep label[root]==root, so concurrent finds stay valid
-    atomicAdd(&size[root], 1);
+    int root = -1;
+    if (p < n && label[p] >= 0) {
+        root = uf_find(label, (int)p);
+        label[p] = root;  // roots keep label[root]==root, so concurrent finds stay valid
+    }
+    // one atomic per distinct root per warp (large regions would otherwise serialise on a single address)
+    const unsigned peers = __match_any_sync(0xffffffffu, root);
+    if (root >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&size[root], __popc(peers));
 }
 __global__ void __launch_bounds__(256) spk_apply_kernel(const int* __restrict__ label, const int* __restrict__ size, size_t n,
                                                         unsigned min_area, float invalid, float* __restrict__ disp) {

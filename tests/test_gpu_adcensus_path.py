@@ -159,6 +159,11 @@ def test_cross_aggregate_fast_within_tolerance(engine, oracle, H, W, D, kind, se
         got = engine.aggregate_cross(p["bgr_left"], cost, iters=iters, mode=SUM_FAST)["cost"]
         err, same = rel_err(got, refk)
         assert err <= 1e-5, f"iters={iters}: max rel err {err:.3e} ({same:.2%} bit-identical)"
+    # inputs with negative values take the general (TwoSum) prefix instead of the compensated non-negative one
+    ncost = cost - np.float32(0.75)
+    rn = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], ncost, iters=2)["cost"]
+    gn = engine.aggregate_cross(p["bgr_left"], ncost, iters=2, mode=SUM_FAST)["cost"]
+    assert np.abs(gn - rn).max() <= 1e-5 * max(1.0, float(np.abs(rn).max()))
     # integer-valued input: the first iteration is exact under any summation order
     icost = np.rint(cost * 100).astype(np.float32)
     r1 = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], icost, iters=1)["cost"]
