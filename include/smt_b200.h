@@ -117,6 +117,38 @@ SMT_API smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const
                                          int32_t iters, smt_sum_mode_t mode, float* cost_out, uint8_t* arms_out,
                                          uint16_t* sup_hfirst, uint16_t* sup_vfirst, smt_memspace_t space);
 
+/* ------------------------------------------------------------------------------------------------ CrossArm / CBLSM
+ * smt_ad_cost replaces CBLSM's ComputeAD / ComputeADRight (CBLSM/CBLSM.h:327, :355) and AD_Census::ComputeAD[Right]
+ * (AD-CensusV1/AD-Census.h:75, :103): left/right uint8 [rows][cols], ad float32 [rows][cols][D].
+ *
+ * smt_arms_gray replaces the four arm-length passes of
+ *   variant 0: CrossArmAggregation::Compute{Left,Right,Top,Button}ArmLength (AD-CensusV1/CrossArm.cpp:147-598), run in
+ *              main.cpp:69-72 order with ONE member threshold that drops to 6 for good once any arm passes 17 pixels,
+ *              and with the Right pass's `col = _row` indexing (:265) -- requires rows <= cols; pass max_length=34,
+ *              sec_length=17 (hard-coded in the reference);
+ *   variant 1: CBLSM ArmLength{L,R,Up,Down} (CBLSM/CBLSM.h:643, :536, :753, :861): the threshold is a by-value uchar,
+ *              so each of the four calls starts again from `tao`.
+ * img: uint8 [rows][cols][channels], channels 1 or 3.  Outputs int32 [rows][cols] (any may be NULL).
+ * tao_final (optional, HOST pointer in both memspaces): the threshold the reference object is left with (variant 0).
+ *
+ * smt_aggregate_rect replaces the rectangle-mean aggregations
+ *   variant 0: CrossArmAggregation::AggregationVertical (CrossArm.cpp:60)  -- flat slice index, column-major order
+ *   variant 1: CrossArmAggregation::Aggregation        (CrossArm.cpp:104) -- flat index, exclusive upper bounds
+ *   variant 2: CBLSM costAggregationV5                 (CBLSM/CBLSM.h:1179) -- row-major order
+ * Returns SMT_ERR_UNSUPPORTED when the arm maps address cells outside the slice (the reference reads out of bounds
+ * there).  SMT_SUM_REFERENCE_ORDER is bit-exact; SMT_SUM_FAST uses a double-single summed-area table.
+ */
+SMT_API smt_status_t smt_ad_cost(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols,
+                                 int32_t D, int32_t view, float* ad, smt_memspace_t space);
+SMT_API smt_status_t smt_arms_gray(smt_ctx* ctx, const uint8_t* img, int32_t channels, int32_t rows, int32_t cols,
+                                   int32_t tao, int32_t max_length, int32_t sec_length, int32_t variant,
+                                   int32_t* arm_left, int32_t* arm_right, int32_t* arm_top, int32_t* arm_bottom,
+                                   int32_t* tao_final, smt_memspace_t space);
+SMT_API smt_status_t smt_aggregate_rect(smt_ctx* ctx, const float* vol_in, const int32_t* arm_left,
+                                        const int32_t* arm_right, const int32_t* arm_top, const int32_t* arm_bottom,
+                                        int32_t rows, int32_t cols, int32_t D, int32_t variant, smt_sum_mode_t mode,
+                                        float* vol_out, smt_memspace_t space);
+
 /* ------------------------------------------------------------------------------------------------ ScanlineOptimizer
  * Replaces ScanlineOptimizer::{Initialize, ScanLine, ScanLineLeftRight, ScanLineUpDown, WTA}
  * (AD-CensusV1/ScanlineOptimizer.h:66, :104, :130, :194, :40) including the up/down quirks (:221,:232,:238).

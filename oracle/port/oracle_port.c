@@ -460,3 +460,166 @@ void orc_median(const float* in, float* out, int W, int H, int k) {
         }
     free(w);
 }
+
+/* ------------------------------------------------------------------------------------------------ grey/colour arms
+ * AD-CensusV1/CrossArm.cpp:147-598 (CrossArmAggregation::Compute{Left,Right,Top,Button}ArmLength) and
+ * CBLSM/CBLSM.h:536-966 (ArmLength{R,L,Up,Down}).  One walk per (pixel, direction):
+ *   offsets k = 1, 2, ...; the threshold drops to 6 for good once k exceeds `sec` (the assignment sticks in *tao);
+ *   the arm is capped at `maxlen`; the walk stops at the image border or at the first pixel whose largest channel
+ *   difference exceeds the threshold; a pixel at least two away from the border keeps arm 1 when the very first
+ *   neighbour already fails. */
+static int walk_grey_arm(const uint8_t* img, int ch, long p0, long step, int room, int minrule, int sec, int maxlen,
+                         int* tao) {
+    const uint8_t* c0 = img + (size_t)p0 * ch;
+    int saved = 0, k = 0;
+    while (k <= room) {          /* `while (j - offset >= 0)` with offset == k */
+        saved = k;
+        ++k;
+        if (k > sec) {           /* CrossArm.cpp:168-173 */
+            *tao = 6;
+            if (k > maxlen) break;
+        }
+        if (k <= room) {
+            const uint8_t* c = img + (size_t)(p0 + step * k) * ch;
+            int m = 0;
+            for (int t = 0; t < ch; ++t) {
+                const int dlt = abs((int)c0[t] - (int)c[t]);
+                if (dlt > m) m = dlt;
+            }
+            if (m > *tao) {      /* :184-197 */
+                if (minrule && saved < 1) saved = 1;
+                break;
+            }
+        } else {
+            break;
+        }
+    }
+    return saved;
+}
+
+void orc_cblsm_arms(const uint8_t* img, int ch, int H, int W, int tao0, int maxLength, int secLength, int32_t* armL,
+                    int32_t* armR, int32_t* armUp, int32_t* armDown) {
+    /* `tao` is a by-value uchar parameter: it sticks at 6 only within one call (CBLSM.h:536, :558) */
+    int32_t* outs[4] = {armL, armR, armUp, armDown};
+    for (int dir = 0; dir < 4; ++dir) {
+        if (!outs[dir]) continue;
+        int tao = (uint8_t)tao0;
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const long p = (long)i * W + j;
+                int v;
+                if (dir == 0) v = walk_grey_arm(img, ch, p, -1, j, j - 1 >= 1, secLength, maxLength, &tao);
+                else if (dir == 1) v = walk_grey_arm(img, ch, p, +1, W - 1 - j, j + 1 < W - 1, secLength, maxLength, &tao);
+                else if (dir == 2) v = walk_grey_arm(img, ch, p, -W, i, i - 1 >= 1, secLength, maxLength, &tao);
+                else v = walk_grey_arm(img, ch, p, +W, H - 1 - i, i + 1 < H - 1, secLength, maxLength, &tao);
+                outs[dir][p] = v;
+            }
+    }
+}
+
+/* CrossArmAggregation: `_tao` is a MEMBER, so the drop to 6 survives across pixels and across the four passes, which
+ * main.cpp:69-72 runs in the order Left, Right, Top, Button.  The Right pass uses `col = _row` (CrossArm.cpp:265): it
+ * visits columns j < H only, treats column H as the border and stores at i*H + j.  mode 1 = AggregationVertical
+ * (:60-102), mode 2 = Aggregation (:104-145); both address the slice with a flat index, so a window running past the
+ * end of a row continues in the next one.  Returns the final _tao. */
+int orc_crossarm(const uint8_t* img, int ch, int H, int W, int D, int tao0, int32_t* armL, int32_t* armR, int32_t* armT,
+                 int32_t* armB, int mode, const float* vol_in, float* vol_out) {
+    const size_t npix = (size_t)H * W;
+    int tao = tao0;
+    int32_t* L = (int32_t*)calloc(npix, sizeof(int32_t));
+    int32_t* R = (int32_t*)calloc(npix, sizeof(int32_t));
+    int32_t* T = (int32_t*)calloc(npix, sizeof(int32_t));
+    int32_t* B = (int32_t*)calloc(npix, sizeof(int32_t));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j)
+            L[(size_t)i * W + j] = walk_grey_arm(img, ch, (long)i * W + j, -1, j, j - 1 >= 1, 17, 34, &tao);
+    {
+        const int col = H; /* the bug: col = _row */
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < col; ++j)
+                R[(size_t)i * col + j] =
+                    walk_grey_arm(img, ch, (long)i * W + j, +1, col - 1 - j, j + 1 < col - 1, 17, 34, &tao);
+    }
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j)
+            T[(size_t)i * W + j] = walk_grey_arm(img, ch, (long)i * W + j, -W, i, i - 1 >= 1, 17, 34, &tao);
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j)
+            B[(size_t)i * W + j] = walk_grey_arm(img, ch, (long)i * W + j, +W, H - 1 - i, i + 1 < H - 1, 17, 34, &tao);
+    if (mode) {
+        float* layer = (float*)malloc(npix * sizeof(float));
+        for (int d = 0; d < D; ++d) {
+            for (size_t p = 0; p < npix; ++p) layer[p] = vol_in[p * D + d];
+            for (int i = 0; i < H; ++i)
+                for (int j = 0; j < W; ++j) {
+                    const size_t p = (size_t)i * W + j;
+                    const int l = L[p], r = R[p], up = T[p], down = B[p];
+                    float value = 0;
+                    int number = 0;
+                    if (mode == 1) { /* column-major, inclusive bounds (:88-95) */
+                        for (int a = -l; a <= r; ++a)
+                            for (int b = -up; b <= down; ++b) {
+                                value = value + layer[(long)(i + b) * W + j + a];
+                                ++number;
+                            }
+                    } else { /* row-major, EXCLUSIVE upper bounds (:131-138) */
+                        for (int b = -up; b < down; ++b)
+                            for (int a = -l; a < r; ++a) {
+                                value = value + layer[(long)(i + b) * W + j + a];
+                                ++number;
+                            }
+                    }
+                    vol_out[p * D + d] = value / number;
+                }
+        }
+        free(layer);
+    }
+    if (armL) memcpy(armL, L, npix * sizeof(int32_t));
+    if (armR) memcpy(armR, R, npix * sizeof(int32_t));
+    if (armT) memcpy(armT, T, npix * sizeof(int32_t));
+    if (armB) memcpy(armB, B, npix * sizeof(int32_t));
+    free(L);
+    free(R);
+    free(T);
+    free(B);
+    return tao;
+}
+
+/* ------------------------------------------------------------------------------------------------ CBLSM.h live part */
+/* ComputeAD / ComputeADRight (:327-381): integer |L - R| from uchar images, clamp-by-copy at the border */
+void orc_cblsm_ad(const uint8_t* left, const uint8_t* right, int H, int W, int D, float* adL, float* adR) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j)
+            for (int d = 0; d < D; ++d) {
+                if (adL) adL[VOL(i, j, d)] = (j - d < 0) ? adL[VOL(i, j, d - 1)]
+                                                         : (float)abs((int)left[(size_t)i * W + j] - (int)right[(size_t)i * W + j - d]);
+                if (adR) adR[VOL(i, j, d)] = (j + d >= W) ? adR[VOL(i, j, d - 1)]
+                                                          : (float)abs((int)left[(size_t)i * W + j + d] - (int)right[(size_t)i * W + j]);
+            }
+}
+
+/* costAggregationV5 (:1179-1224): mean over the rectangle spanned by the pixel's four arms, row-major accumulation */
+void orc_cblsm_aggregate_v5(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
+                            const int32_t* armUp, const int32_t* armDown, int D, int H, int W) {
+    const size_t npix = (size_t)H * W;
+    float* layer = (float*)malloc(npix * sizeof(float));
+    for (int d = 0; d < D; ++d) {
+        for (size_t p = 0; p < npix; ++p) layer[p] = vol_in[p * D + d];
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const size_t p = (size_t)i * W + j;
+                float value = 0;
+                int number = 0;
+                for (int b = -armUp[p]; b <= armDown[p]; ++b)
+                    for (int a = -armL[p]; a <= armR[p]; ++a) {
+                        value = value + layer[(long)(i + b) * W + j + a];
+                        ++number;
+                    }
+                vol_out[p * D + d] = value / number;
+            }
+    }
+    free(layer);
+}
+
+/* ComputeDispOringin (:383-407): first minimum, strict '<' */
+void orc_cblsm_wta(const float* vol, float* disp, int D, int H, int W) { orc_wta(vol, H, W, D, disp); }

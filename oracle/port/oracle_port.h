@@ -35,7 +35,15 @@ void orc_median(const float* in, float* out, int W, int H, int k);
 int orc_cross_aggregate(const uint8_t* bgrL, const uint8_t* bgrR, const float* cost_init, int W, int H, int D, int L1,
                         int L2, int t1, int t2, int iters, float* cost_out, uint8_t* arms, uint16_t* sup0,
                         uint16_t* sup1);
-/* (crossarm / CBLSM / SAD / NCC / ASW restatements are appended below as they are pinned) */
+int orc_crossarm(const uint8_t* img, int ch, int H, int W, int D, int tao, int32_t* armL, int32_t* armR,
+                 int32_t* armT, int32_t* armB, int mode, const float* vol_in, float* vol_out);
+void orc_cblsm_ad(const uint8_t* left, const uint8_t* right, int H, int W, int D, float* adL, float* adR);
+void orc_cblsm_arms(const uint8_t* img, int ch, int H, int W, int tao, int maxLength, int secLength, int32_t* armL,
+                    int32_t* armR, int32_t* armUp, int32_t* armDown);
+void orc_cblsm_aggregate_v5(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
+                            const int32_t* armUp, const int32_t* armDown, int D, int H, int W);
+void orc_cblsm_wta(const float* vol, float* disp, int D, int H, int W);
+/* (SAD / NCC / ASW restatements are appended below as they are pinned) */
 
 #ifdef __cplusplus
 }

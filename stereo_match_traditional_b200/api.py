@@ -212,6 +212,42 @@ class Engine:
             res.update(arms=arms, sup0=s0, sup1=s1)
         return res
 
+    # ------------------------------------------------------------------ CrossArm / CBLSM
+    def ad_cost(self, left, right, D, view=0):
+        """CBLSM ComputeAD (view 0) / ComputeADRight (view 1) from uint8 grey images."""
+        a = _Args(self, left, right)
+        H, W = left.shape
+        pl = a.inp(left, np.uint8, (H, W))
+        pr = a.inp(right, np.uint8, (H, W))
+        out, po = a.out((H, W, D), np.float32)
+        self._ck(self.lib.smt_ad_cost(self.h, pl, pr, H, W, D, view, po, a.space))
+        return out
+
+    def arms_gray(self, img, tao, max_length=34, sec_length=17, variant=0):
+        """variant 0: CrossArmAggregation's four passes (sticky member threshold, Right-pass quirk); 1: CBLSM ArmLength*."""
+        a = _Args(self, img)
+        ch = 3 if img.ndim == 3 else 1
+        H, W = img.shape[:2]
+        pi = a.inp(img, np.uint8)
+        outs = [a.out((H, W), np.int32) for _ in range(4)]
+        tf = C.c_int32(0)
+        self._ck(self.lib.smt_arms_gray(self.h, pi, ch, H, W, int(tao), int(max_length), int(sec_length), int(variant),
+                                        *[o[1] for o in outs], C.byref(tf), a.space))
+        names = ("left", "right", "top", "bottom") if variant == 0 else ("left", "right", "up", "down")
+        res = {n: o[0] for n, o in zip(names, outs)}
+        res["tao_final"] = int(tf.value)
+        return res
+
+    def aggregate_rect(self, vol, arm_left, arm_right, arm_top, arm_bottom, variant=0, mode=SUM_REFERENCE_ORDER):
+        """variant 0: AggregationVertical, 1: Aggregation (CrossArm.cpp:60,104), 2: costAggregationV5 (CBLSM.h:1179)."""
+        a = _Args(self, vol, arm_left)
+        H, W, D = vol.shape
+        pv = a.inp(vol, np.float32)
+        ps = [a.inp(x, np.int32, (H, W)) for x in (arm_left, arm_right, arm_top, arm_bottom)]
+        out, po = a.out((H, W, D), np.float32)
+        self._ck(self.lib.smt_aggregate_rect(self.h, pv, *ps, H, W, D, int(variant), int(mode), po, a.space))
+        return out
+
     # ------------------------------------------------------------------ ScanlineOptimizer
     def scanline(self, cost, gray, p1=10, p2=150, want: Sequence[str] = ("sum", "disp")):
         a = _Args(self, cost, gray)
