@@ -179,6 +179,32 @@ SMT_API smt_status_t smt_remove_speckles(smt_ctx* ctx, float* disp, int32_t cols
 SMT_API smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32_t cols, int32_t rows,
                                 int32_t wnd_size, smt_memspace_t space);
 
+/* ------------------------------------------------------------------------------------------------ window matchers
+ * smt_sad replaces GetPointDepthLeft / GetPointDepthRight with sadvalue, OptimalDisparity, GetMinSadIndex
+ * (SAD/Sad.h:96, :141, :15, :40, :22).  Inputs are the replicate-padded grey images [rows_padded][cols_padded],
+ * pad = winsize+1 per side (SADmain.cpp:47-48); disp: int32 [rows_padded-2*pad][cols_padded-2*pad] (CV_32S);
+ * costs (optional): float32 [..][..][D], the per-disparity SAD vector incl. the copy-previous rule (:125-129).
+ *
+ * smt_ncc replaces NCC_algorithem with ComputeCost and WinTakeAll (NCC/NCC.h:69, :15, :53): unpadded grey images
+ * [rows][cols]; disp int32 [rows][cols], 0 outside the interior.
+ *
+ * smt_asw replaces AdaptiveSupportWeight / AdaptiveSupportWeightRight with getGausssianMask, getColorMask,
+ * bilateralfiterWight, WinTakeAll (ASW/ASW.h:329, :382, :16, :41, :210, :193): replicate-padded grey images, pad =
+ * win_size+1 (ASWeight.cpp:54-55); disp float32 [rows_padded-2*pad][cols_padded-2*pad].  In the right view the last
+ * win_size+2 output columns are undefined in the reference (it reads costVolume[-1], ASW.h:401,:424); they are 0 here.
+ * smt_asw_crosscheck replaces CrossCheckDiaparity (ASW.h:108): out uint8 [rows][cols].
+ */
+SMT_API smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded,
+                             int32_t cols_padded, int32_t D, int32_t winsize, int32_t right_view, int32_t* disp,
+                             float* costs, smt_memspace_t space);
+SMT_API smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols,
+                             int32_t win_size, int32_t D, int32_t* disp, smt_memspace_t space);
+SMT_API smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded,
+                             int32_t cols_padded, int32_t win_size, int32_t D, double space_sigma, double color_sigma,
+                             int32_t T, int32_t right_view, float* disp, smt_memspace_t space);
+SMT_API smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, const float* disp_right, int32_t rows,
+                                        int32_t cols, uint8_t* out, smt_memspace_t space);
+
 /* ------------------------------------------------------------------------------------------------ full pipeline
  * P_full: the composition of the reference entry points above with the reference's own
  * default parameters (main.cpp:24-30, adcensus_types.h:69-70).

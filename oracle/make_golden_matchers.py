@@ -1,0 +1,68 @@
+"""ORACLE tooling: golden fixtures for the CrossArm / CBLSM / SAD / NCC / ASW paths (called by oracle/make_golden.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+from stereo_match_traditional_b200.synth import make_pair, replicate_pad
+
+# (name, H, W, D, kind, seed)
+MATCHER_CASES = [
+    ("mat_scene_30x80x16", 30, 80, 16, "scene", 201),
+    ("mat_noise_24x60x40", 24, 60, 40, "noise", 202),
+    ("mat_const_20x50x8", 20, 50, 8, "constant", 203),
+]
+CROSSARM_CASES = [
+    ("ca_scene_48x200x4", 48, 200, 4, "scene", 211),
+    ("ca_noise_50x220x3", 50, 220, 3, "noise", 212),
+]
+
+
+def matcher_outputs(o, H, W, D, kind, seed):
+    p = make_pair(H, W, D, seed, kind)
+    gl, gr = p["gray_left"], p["gray_right"]
+    out = {}
+    lp, rp = replicate_pad(gl, 4), replicate_pad(gr, 4)     # SAD winsize 3 -> pad 4 (SADmain.cpp:33-48)
+    out["sad_left"] = o.sad(lp, rp, D, 3)
+    out["sad_right"] = o.sad(lp, rp, D, 3, True)
+    out["sad_costs_left"] = o.sad_costs_left(lp, rp, D, 3)
+    out["ncc_w4"] = o.ncc(gl, gr, D, 4)
+    la, ra = replicate_pad(gl, 4), replicate_pad(gr, 4)     # ASW winSize 3 -> pad 4
+    out["asw_left"] = o.asw(la, ra, D, 3, 50, 30, 40)
+    asw_r = o.asw(la, ra, D, 3, 50, 30, 40, True)
+    out["asw_right_defined"] = np.ascontiguousarray(asw_r[:, : W - 3 - 2])   # ASW.h:401 reads costVolume[-1] beyond
+    out["asw_crosscheck"] = o.asw_crosscheck(out["asw_left"], np.zeros_like(out["asw_left"]))
+    return out
+
+
+def crossarm_outputs(o, H, W, D, kind, seed):
+    p = make_pair(H, W, D, seed, kind)
+    out = {}
+    vol = np.random.default_rng(seed).random((H, W, D), dtype=np.float32)
+    for tag, img in (("gray", p["gray_left"]), ("bgr", p["bgr_left"])):
+        a = o.crossarm(img, D, 30, 1, vol)
+        for k in ("left", "right", "top", "bottom"):
+            out[f"crossarm_{tag}_{k}"] = a[k]
+        out[f"crossarm_{tag}_tao"] = np.array([a["tao_final"]], np.int32)
+        out[f"crossarm_{tag}_aggv"] = a["vol"]
+        c = o.cblsm_arms(img, 25, 34, 17)
+        for k in ("left", "right", "up", "down"):
+            out[f"cblsm_{tag}_{k}"] = c[k]
+    adL, adR = o.cblsm_ad(p["gray_left"], p["gray_right"], D)
+    out["cblsm_adL"], out["cblsm_adR"] = adL, adR
+    arms = o.cblsm_arms(p["gray_left"], 25, 34, 17)
+    v1 = o.cblsm_aggregate_v5(adL, arms)
+    out["cblsm_v5_1"] = v1
+    out["cblsm_v5_2"] = o.cblsm_aggregate_v5(v1, arms)
+    out["cblsm_wta"] = o.cblsm_wta(out["cblsm_v5_2"])
+    return out
+
+
+def generate(o, golden_dir, digests, digest):
+    for name, H, W, D, kind, seed in MATCHER_CASES:
+        out = matcher_outputs(o, H, W, D, kind, seed)
+        digests[name] = {"shape": [H, W, D], "kind": kind, "seed": seed, "outputs": {k: digest(v) for k, v in out.items()}}
+    for name, H, W, D, kind, seed in CROSSARM_CASES:
+        out = crossarm_outputs(o, H, W, D, kind, seed)
+        digests[name] = {"shape": [H, W, D], "kind": kind, "seed": seed, "outputs": {k: digest(v) for k, v in out.items()}}
+    small = matcher_outputs(o, *MATCHER_CASES[0][1:])
+    np.savez_compressed(golden_dir / f"{MATCHER_CASES[0][0]}.npz", **small)

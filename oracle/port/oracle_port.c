@@ -623,3 +623,196 @@ void orc_cblsm_aggregate_v5(const float* vol_in, float* vol_out, const int32_t* 
 
 /* ComputeDispOringin (:383-407): first minimum, strict '<' */
 void orc_cblsm_wta(const float* vol, float* disp, int D, int H, int W) { orc_wta(vol, H, W, D, disp); }
+
+/* ------------------------------------------------------------------------------------------------ SAD (SAD/Sad.h)
+ * Inputs are replicate-padded grey images [Hp][Wp], pad w = winsize+1 per side (SADmain.cpp:47-48). */
+static float sad_window(const uint8_t* A, const uint8_t* B, int Wp, int ai, int aj, int bi, int bj, int k) {
+    int s = 0; /* sadvalue (:15-20): cv::abs(a-b) is absdiff for 8-bit, cv::sum -> int -> float */
+    for (int y = 0; y < k; ++y)
+        for (int x = 0; x < k; ++x) s += abs((int)A[(size_t)(ai + y) * Wp + aj + x] - (int)B[(size_t)(bi + y) * Wp + bj + x]);
+    return (float)s;
+}
+
+/* OptimalDisparity (:40-85) */
+float orc_sad_optimal_disparity(const float* sad, int D) {
+    float minv = 65535.f, best = 65535.f, sec = sad[0];
+    for (int i = 1; i < D; ++i)
+        if (minv > sad[i]) {
+            minv = sad[i];
+            best = (float)i;
+        }
+    for (int i = 0; i < D; ++i)
+        if (minv != sad[i]) sec = sad[i] < sec ? sad[i] : sec;
+    if (sec - minv <= 0.01) return 0; /* float difference compared with the double 0.01 (:66) */
+    if (best == 0 || best == D - 1) return 0;
+    return best; /* the sub-pixel value (:76-81) is computed and discarded */
+}
+
+void orc_sad_costs_left(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, float* costs) {
+    const int w = winsize + 1, k = 2 * w + 1, W = Wp - 2 * w;
+    for (int i = w; i < Hp - w; ++i)
+        for (int j = w; j < Wp - w; ++j) {
+            float* s = costs + ((size_t)(i - w) * W + (j - w)) * D;
+            for (int d = 0; d < D; ++d) /* :121-132 */
+                s[d] = (j - w - d < 0) ? s[d - 1] : sad_window(Lp, Rp, Wp, i - w, j - w, i - w, j - w - d, k);
+        }
+}
+
+void orc_sad_left(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, int32_t* disp) {
+    const int w = winsize + 1, k = 2 * w + 1, W = Wp - 2 * w;
+    float* s = (float*)malloc((size_t)D * sizeof(float));
+    for (int i = w; i < Hp - winsize - 1; ++i) /* :110-116 */
+        for (int j = w; j < Wp - winsize - 1; ++j) {
+            for (int d = 0; d < D; ++d)
+                s[d] = (j - w - d < 0) ? s[d - 1] : sad_window(Lp, Rp, Wp, i - w, j - w, i - w, j - w - d, k);
+            disp[(size_t)(i - w) * W + (j - w)] = (int32_t)orc_sad_optimal_disparity(s, D);
+        }
+    free(s);
+}
+
+/* GetPointDepthRight (:141-182): the loops stop one row and one column early (:154-160); GetMinSadIndex (:22-38) */
+void orc_sad_right(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, int32_t* disp) {
+    const int w = winsize + 1, k = 2 * w + 1, W = Wp - 2 * w;
+    float* s = (float*)malloc((size_t)D * sizeof(float));
+    for (int i = w; i < Hp - w - 1; ++i)
+        for (int j = w; j < Wp - w - 1; ++j) {
+            for (int d = 0; d < D; ++d)
+                s[d] = (j + d + w + 1 > Wp) ? s[d - 1] : sad_window(Lp, Rp, Wp, i - w, j - w + d, i - w, j - w, k);
+            float m = s[0];
+            int idx = 0;
+            for (int d = 1; d < D; ++d)
+                if (s[d] < m) {
+                    m = s[d];
+                    idx = d;
+                }
+            disp[(size_t)(i - w) * W + (j - w)] = idx;
+        }
+    free(s);
+}
+
+/* ------------------------------------------------------------------------------------------------ NCC (NCC/NCC.h) */
+/* ComputeCost (:15-49): means first, then centred sums, all in double, in the reference's loop order */
+double orc_ncc_cost(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int i, int j, int d) {
+    (void)H;
+    const int k = 2 * winSize + 1, n = k * k;
+    const uint8_t* a = L + (size_t)(i - winSize) * W + (j - winSize);
+    const uint8_t* b = R + (size_t)(i - winSize) * W + (j - winSize - d);
+    double lm = 0, rm = 0, ls = 0, rs = 0, num = 0;
+    for (int y = 0; y < k; ++y)
+        for (int x = 0; x < k; ++x) { /* the reference indexes (j,i) here; the window is square (:29-30) */
+            lm += a[(size_t)x * W + y];
+            rm += b[(size_t)x * W + y];
+        }
+    lm /= n;
+    rm /= n;
+    for (int y = 0; y < k; ++y)
+        for (int x = 0; x < k; ++x) {
+            const double dl = a[(size_t)y * W + x] - lm, dr = b[(size_t)y * W + x] - rm;
+            ls += pow(dl, 2);
+            rs += pow(dr, 2);
+            num += dl * dr;
+        }
+    return num / (sqrt(ls) * sqrt(rs));
+}
+
+/* NCC_algorithem (:69-95) with WinTakeAll (:53-67): arg-max whose running maximum is rounded to float; a disparity
+ * whose window leaves the image scores `invalid` = 255 (:7,:88), which beats every correlation */
+void orc_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int D, int32_t* disp) {
+    double* cost = (double*)malloc((size_t)D * sizeof(double));
+    for (int i = winSize; i < H - winSize; ++i)
+        for (int j = winSize; j < W - winSize; ++j) {
+            for (int d = 0; d < D; ++d) cost[d] = (j - winSize - d >= 0) ? orc_ncc_cost(L, R, H, W, winSize, i, j, d) : 255.0;
+            int best = 0;
+            float m = (float)cost[0];
+            for (int d = 1; d < D; ++d)
+                if (m < cost[d]) {
+                    best = d;
+                    m = (float)cost[d];
+                }
+            disp[(size_t)i * W + j] = best;
+        }
+    free(cost);
+}
+
+/* ------------------------------------------------------------------------------------------------ ASW (ASW/ASW.h) */
+void orc_asw_masks(int winSize, double spaceSigma, double colorSigma, double* space_out, double* color_out) {
+    const int k = 2 * winSize + 3, c = (k - 1) / 2;
+    for (int i = 0; i < k; ++i) /* getGausssianMask (:16-35) */
+        for (int j = 0; j < k; ++j)
+            space_out[i * k + j] = exp(-(pow(j - c, 2) + pow(i - c, 2)) / (2 * spaceSigma * spaceSigma));
+    for (int i = 0; i < 256; ++i) color_out[i] = exp(-(i * i) / (2 * colorSigma * colorSigma)); /* getColorMask (:41-47) */
+}
+
+/* bilateralfiterWight (:210-257) on two k x k windows */
+static float asw_cost(const uint8_t* A, const uint8_t* B, int Wp, int k, int T, const double* space, const double* color) {
+    const int c = (k - 1) / 2;
+    const int ca = A[(size_t)c * Wp + c], cb = B[(size_t)c * Wp + c];
+    double sw = 0, sv = 0;
+    for (int y = 0; y < k; ++y)
+        for (int x = 0; x < k; ++x) {
+            const int pa = A[(size_t)y * Wp + x], pb = B[(size_t)y * Wp + x];
+            const double m0 = color[abs(pa - ca)] * space[y * k + x];
+            const double m1 = color[abs(pb - cb)] * space[y * k + x];
+            const double m2 = m0 * m1;
+            int e = abs(pa - pb);
+            if (e > T) e = T; /* :359-366 */
+            sw += m2;
+            sv += m2 * (double)e;
+        }
+    return (float)(sv / sw);
+}
+
+/* AdaptiveSupportWeight (:329-378) / AdaptiveSupportWeightRight (:382-431) + WinTakeAll (:193-208).  In the right view
+ * the last winSize+2 output columns are invalid at d = 0 and the reference reads costVolume[-1] there (UB); this
+ * restatement leaves those pixels at 0 and parity excludes them. */
+void orc_asw(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, int D, double spaceSigma, double colorSigma,
+             int T, int right_view, float* disp) {
+    const int wins = winSize + 1, k = 2 * wins + 1, W = Wp - 2 * wins;
+    double* space = (double*)malloc((size_t)k * k * sizeof(double));
+    double color[256];
+    orc_asw_masks(winSize, spaceSigma, colorSigma, space, color);
+    float* cost = (float*)malloc((size_t)D * sizeof(float));
+    for (int i = wins; i < Hp - wins; ++i)
+        for (int j = wins; j < Wp - wins; ++j) {
+            int ok = 1;
+            for (int d = 0; d < D; ++d) {
+                int valid;
+                const uint8_t *a, *b;
+                if (!right_view) {
+                    valid = j - wins - d >= 0;
+                    a = Lp + (size_t)(i - wins) * Wp + (j - wins);
+                    b = Rp + (size_t)(i - wins) * Wp + (j - wins - d);
+                } else {
+                    valid = j + wins + d + 1 < Wp - wins;
+                    a = Rp + (size_t)(i - wins) * Wp + (j - wins);
+                    b = Lp + (size_t)(i - wins) * Wp + (j - wins + d);
+                }
+                if (valid) cost[d] = asw_cost(a, b, Wp, k, T, space, color);
+                else if (d == 0) { ok = 0; break; }
+                else cost[d] = cost[d - 1];
+            }
+            float best = 0;
+            if (ok) {
+                float m = cost[0];
+                for (int d = 1; d < D; ++d)
+                    if (m > cost[d]) {
+                        best = (float)d;
+                        m = cost[d];
+                    }
+            }
+            disp[(size_t)(i - wins) * W + (j - wins)] = best;
+        }
+    free(space);
+    free(cost);
+}
+
+/* CrossCheckDiaparity (:108-145) */
+void orc_asw_crosscheck(const float* dispL, const float* dispR, int H, int W, uint8_t* out) {
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const int lv = (int)dispL[(size_t)i * W + j];
+            const float rv = dispR[(size_t)i * W + j - lv];
+            const float diff = fabsf((float)lv - rv);
+            out[(size_t)i * W + j] = diff > 5 ? 0 : (uint8_t)lv;
+        }
+}

@@ -43,7 +43,16 @@ void orc_cblsm_arms(const uint8_t* img, int ch, int H, int W, int tao, int maxLe
 void orc_cblsm_aggregate_v5(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
                             const int32_t* armUp, const int32_t* armDown, int D, int H, int W);
 void orc_cblsm_wta(const float* vol, float* disp, int D, int H, int W);
-/* (SAD / NCC / ASW restatements are appended below as they are pinned) */
+void orc_sad_left(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, int32_t* disp);
+void orc_sad_right(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, int32_t* disp);
+void orc_sad_costs_left(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int D, int winsize, float* costs);
+float orc_sad_optimal_disparity(const float* sad, int D);
+void orc_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int D, int32_t* disp);
+double orc_ncc_cost(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int i, int j, int d);
+void orc_asw(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, int D, double spaceSigma,
+             double colorSigma, int T, int right_view, float* disp);
+void orc_asw_masks(int winSize, double spaceSigma, double colorSigma, double* space_out, double* color_out);
+void orc_asw_crosscheck(const float* dispL, const float* dispR, int H, int W, uint8_t* out);
 
 #ifdef __cplusplus
 }

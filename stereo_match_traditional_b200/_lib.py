@@ -78,6 +78,10 @@ SIGNATURES = {
     "smt_lrcheck_and": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _i32p, _vp, _i32p, _i]),
     "smt_remove_speckles": (_i, [_vp, _vp, _i, _i, _i, C.c_uint32, _i, _i]),
     "smt_median": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
+    "smt_sad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i]),
+    "smt_ncc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "smt_asw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _i, _i, _vp, _i]),
+    "smt_asw_crosscheck": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
     "smt_adcensus_default_params": (None, [C.POINTER(AdCensusParams), _i, _i, _i]),
     "smt_pipeline_adcensus_full": (_i, [_vp, C.POINTER(AdCensusParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
 }

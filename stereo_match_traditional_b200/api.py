@@ -309,6 +309,50 @@ class Engine:
         self._ck(self.lib.smt_median(self.h, pi, po, W, H, int(k), a.space))
         return out
 
+    # ------------------------------------------------------------------ window matchers
+    def sad(self, left_padded, right_padded, D, winsize=3, right_view=False, want_costs=False):
+        """GetPointDepthLeft / GetPointDepthRight (SAD/Sad.h:96,141) on replicate-padded grey images (pad = winsize+1)."""
+        a = _Args(self, left_padded, right_padded)
+        Hp, Wp = left_padded.shape
+        pad = winsize + 1
+        pl = a.inp(left_padded, np.uint8, (Hp, Wp))
+        pr = a.inp(right_padded, np.uint8, (Hp, Wp))
+        disp, pd = a.out((Hp - 2 * pad, Wp - 2 * pad), np.int32)
+        costs, pc = a.out((Hp - 2 * pad, Wp - 2 * pad, D), np.float32, want_costs)
+        self._ck(self.lib.smt_sad(self.h, pl, pr, Hp, Wp, D, winsize, int(bool(right_view)), pd, pc, a.space))
+        return (disp, costs) if want_costs else disp
+
+    def ncc(self, left, right, D, win_size=10):
+        """NCC_algorithem (NCC/NCC.h:69)."""
+        a = _Args(self, left, right)
+        H, W = left.shape
+        pl = a.inp(left, np.uint8, (H, W))
+        pr = a.inp(right, np.uint8, (H, W))
+        disp, pd = a.out((H, W), np.int32)
+        self._ck(self.lib.smt_ncc(self.h, pl, pr, H, W, win_size, D, pd, a.space))
+        return disp
+
+    def asw(self, left_padded, right_padded, D, win_size=11, space_sigma=50.0, color_sigma=30.0, T=40, right_view=False):
+        """AdaptiveSupportWeight / AdaptiveSupportWeightRight (ASW/ASW.h:329,382) on replicate-padded grey images."""
+        a = _Args(self, left_padded, right_padded)
+        Hp, Wp = left_padded.shape
+        pad = win_size + 1
+        pl = a.inp(left_padded, np.uint8, (Hp, Wp))
+        pr = a.inp(right_padded, np.uint8, (Hp, Wp))
+        disp, pd = a.out((Hp - 2 * pad, Wp - 2 * pad), np.float32)
+        self._ck(self.lib.smt_asw(self.h, pl, pr, Hp, Wp, win_size, D, float(space_sigma), float(color_sigma), int(T),
+                                  int(bool(right_view)), pd, a.space))
+        return disp
+
+    def asw_crosscheck(self, disp_left, disp_right):
+        a = _Args(self, disp_left, disp_right)
+        H, W = disp_left.shape
+        pl = a.inp(disp_left, np.float32, (H, W))
+        pr = a.inp(disp_right, np.float32, (H, W))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_asw_crosscheck(self.h, pl, pr, H, W, po, a.space))
+        return out
+
     # ------------------------------------------------------------------ full pipeline
     def default_params(self, H, W, D) -> AdCensusParams:
         p = AdCensusParams()

@@ -1,0 +1,454 @@
+// Window matchers: SAD (SAD/Sad.h), NCC (NCC/NCC.h) and adaptive support weight (ASW/ASW.h).
+//
+//   SAD / NCC  the per-disparity window sum (|l-r| resp. l*r) is a separable box sum.  box_sum_kernel stages a band of
+//              image rows in shared memory, each thread owns one (column, disparity) pair, forms the horizontal
+//              (2w+1)-tap sum of a row from shared memory and slides the vertical window with a ring of the last 2w+1
+//              row sums -- O(2w+1) taps per cell instead of (2w+1)^2, all in exact integer arithmetic.  NCC's other four
+//              sums (sum l, sum l^2, sum r, sum r^2) do not depend on d and are per-pixel maps.
+//   ASW        bilateral support weights are not separable: 625 taps per cell from shared-memory tiles, with the
+//              reference pixel's weight table computed once per pixel and reused for all disparities.
+#include <cmath>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- separable box sums
+constexpr int BOX_TX = 4, BOX_TD = 64, BOX_RB = 64;  // columns x disparities per block, rows per band
+
+// A: the view's own padded image, B: the other image, both [Hp][Wp] uint8.  sign -1: other window at column -d
+// (left view), +1: at column +d (right view).  out: int32 [Ho][Wo][D], Ho = Hp-2w, Wo = Wp-2w; cells whose other
+// window leaves the image get -1 (Sad.h:125,:167; NCC.h:81).
+template <int MODE>  // 0: |a-b| (Sad.h:15-20), 1: a*b
+__global__ void __launch_bounds__(BOX_TX* BOX_TD) box_sum_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B,
+                                                                  int Hp, int Wp, int w, int sign, int D, int* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = 2 * w + 1;
+    const int Ho = Hp - 2 * w, Wo = Wp - 2 * w;
+    const int own_w = BOX_TX + 2 * w, oth_w = BOX_TX + 2 * w + BOX_TD - 1, rows = BOX_RB + 2 * w;
+    int* ring = reinterpret_cast<int*>(smem_raw);                                   // [K][256]
+    uint8_t* s_own = reinterpret_cast<uint8_t*>(ring + (size_t)K * BOX_TX * BOX_TD);  // [rows][own_w]
+    uint8_t* s_oth = s_own + (size_t)rows * own_w;                                  // [rows][oth_w]
+
+    const int jo0 = blockIdx.x * BOX_TX, io0 = blockIdx.y * BOX_RB, d0 = blockIdx.z * BOX_TD;
+    const int tid = threadIdx.x, xl = tid / BOX_TD, dl = tid % BOX_TD;
+    const int oth_base = sign < 0 ? jo0 - (d0 + BOX_TD - 1) : jo0 + d0;  // padded column of s_oth[.][0]
+    for (int t = tid; t < rows * own_w; t += blockDim.x) {
+        const int r = t / own_w, c = t - r * own_w;
+        const int y = io0 + r, x = jo0 + c;
+        s_own[t] = (y < Hp && x < Wp) ? A[(size_t)y * Wp + x] : 0;
+    }
+    for (int t = tid; t < rows * oth_w; t += blockDim.x) {
+        const int r = t / oth_w, c = t - r * oth_w;
+        const int y = io0 + r, x = oth_base + c;
+        s_oth[t] = (y < Hp && x >= 0 && x < Wp) ? B[(size_t)y * Wp + x] : 0;
+    }
+    __syncthreads();
+
+    const int jo = jo0 + xl, d = d0 + dl;
+    const int oth_off = sign < 0 ? xl + (BOX_TD - 1 - dl) : xl + dl;
+    const bool valid = sign < 0 ? (jo - d >= 0) : (jo + 2 * w + d <= Wp - 1);
+    const bool in_range = jo < Wo && d < D;
+    int acc = 0;
+    for (int pr = 0; pr < rows; ++pr) {
+        const uint8_t* a = s_own + (size_t)pr * own_w + xl;
+        const uint8_t* b = s_oth + (size_t)pr * oth_w + oth_off;
+        int hs = 0;
+        for (int t = 0; t < K; ++t) {
+            const int va = a[t], vb = b[t];
+            hs += MODE == 0 ? abs(va - vb) : va * vb;
+        }
+        int* slot = ring + (size_t)(pr % K) * (BOX_TX * BOX_TD) + tid;
+        if (pr >= K) acc -= *slot;
+        acc += hs;
+        *slot = hs;
+        const int io = io0 + pr - (K - 1);
+        if (pr >= K - 1 && io < Ho && in_range) out[((size_t)io * Wo + jo) * D + d] = valid ? acc : -1;
+    }
+}
+
+static smt_status_t k_box_sum(smt_ctx* ctx, int mode, const uint8_t* A, const uint8_t* B, int Hp, int Wp, int w, int sign, int D,
+                              int* out) {
+    const int K = 2 * w + 1, Ho = Hp - 2 * w, Wo = Wp - 2 * w;
+    const size_t smem = sizeof(int) * (size_t)K * BOX_TX * BOX_TD + (size_t)(BOX_RB + 2 * w) * (BOX_TX + 2 * w) +
+                        (size_t)(BOX_RB + 2 * w) * (BOX_TX + 2 * w + BOX_TD - 1);
+    if (smem > 200 * 1024) return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "window radius %d too large for the box-sum tile", w);
+    dim3 grid(cdiv(Wo, BOX_TX), cdiv(Ho, BOX_RB), cdiv(D, BOX_TD));
+    if (mode == 0) {
+        if (smem > 48 * 1024) SMT_CUDA(ctx, cudaFuncSetAttribute(box_sum_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMT_LAUNCH(ctx, box_sum_kernel<0>, grid, BOX_TX * BOX_TD, smem, A, B, Hp, Wp, w, sign, D, out);
+    } else {
+        if (smem > 48 * 1024) SMT_CUDA(ctx, cudaFuncSetAttribute(box_sum_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMT_LAUNCH(ctx, box_sum_kernel<1>, grid, BOX_TX * BOX_TD, smem, A, B, Hp, Wp, w, sign, D, out);
+    }
+    return SMT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- SAD winner selection
+// One thread per output pixel.  Left view: OptimalDisparity (Sad.h:40-85); right view: GetMinSadIndex (:22-38) and
+// the loops that stop one row / column early (:154-160).  costs (optional): float [Ho][Wo][D] with the reference's
+// copy-previous rule for invalid disparities (:125-129).
+__global__ void __launch_bounds__(128) sad_select_kernel(const int* __restrict__ vol, int Ho, int Wo, int D, int right_view,
+                                                         int* __restrict__ disp, float* __restrict__ costs) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (size_t)Ho * Wo) return;
+    const int io = (int)(p / Wo), jo = (int)(p - (size_t)io * Wo);
+    const int* s = vol + p * D;
+    int result = 0;
+    if (!right_view) {
+        float minv = 65535.f, best = 65535.f, last = 0.f;
+        const float s0 = (float)s[0];
+        for (int i = 0; i < D; ++i) {
+            const int raw = s[i];
+            const float v = raw >= 0 ? (float)raw : last;
+            last = v;
+            if (costs) costs[p * D + i] = v;
+            if (i >= 1 && minv > v) {
+                minv = v;
+                best = (float)i;
+            }
+        }
+        float sec = s0;
+        last = 0.f;
+        for (int i = 0; i < D; ++i) {
+            const int raw = s[i];
+            const float v = raw >= 0 ? (float)raw : last;
+            last = v;
+            if (minv != v) sec = fminf(sec, v);
+        }
+        if ((double)(sec - minv) <= 0.01)
+            result = 0;
+        else if (best == 0.f || best == (float)(D - 1))
+            result = 0;
+        else
+            result = (int)best;
+    } else {
+        if (io >= Ho - 1 || jo >= Wo - 1) {
+            disp[p] = 0;  // never written by the reference: stays Mat::zeros
+            return;
+        }
+        float m = (float)s[0];
+        int idx = 0;
+        for (int i = 1; i < D; ++i) {
+            const int raw = s[i];
+            if (raw >= 0 && (float)raw < m) {
+                m = (float)raw;
+                idx = i;
+            }
+        }
+        result = idx;
+    }
+    disp[p] = result;
+}
+
+// ---------------------------------------------------------------------------------------------- NCC
+// per-pixel window sums of v and v^2 (window centred on the pixel, only where it fits)
+__global__ void __launch_bounds__(128) ncc_stats_kernel(const uint8_t* __restrict__ img, int H, int W, int w, int* __restrict__ s1,
+                                                        int* __restrict__ s2) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= W) return;
+    int a = 0, b = 0;
+    if (i >= w && i < H - w && j >= w && j < W - w) {
+        for (int y = -w; y <= w; ++y)
+            for (int x = -w; x <= w; ++x) {
+                const int v = img[(size_t)(i + y) * W + j + x];
+                a += v;
+                b += v * v;
+            }
+    }
+    s1[(size_t)i * W + j] = a;
+    s2[(size_t)i * W + j] = b;
+}
+
+// One warp per interior pixel.  cost(d) = (n*Slr - Sl*Sr) / (sqrt(n*Sll - Sl^2) * sqrt(n*Srr - Sr^2)) from exact
+// integers, then NCC.h:53-67: best = 0, m = float(cost[0]); for d >= 1: if (double)m < cost[d] { best = d; m = float(cost[d]) }.
+// m always equals float(running maximum), so d is accepted iff cost[d] > (double)float(max_{k<d} cost[k]) and the answer
+// is the LAST accepted d: a prefix-max scan instead of a sequential fold.  An out-of-image window scores 255 (:7,:88).
+__global__ void __launch_bounds__(256) ncc_select_kernel(const int* __restrict__ slr, const int* __restrict__ l1,
+                                                         const int* __restrict__ l2, const int* __restrict__ r1,
+                                                         const int* __restrict__ r2, int H, int W, int w, int D,
+                                                         int* __restrict__ disp) {
+    const int Ho = H - 2 * w, Wo = W - 2 * w;
+    const size_t q = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= (size_t)Ho * Wo) return;
+    const int lane = threadIdx.x & 31;
+    const int io = (int)(q / Wo), jo = (int)(q - (size_t)io * Wo);
+    const int i = io + w, j = jo + w;
+    const long long n = (long long)(2 * w + 1) * (2 * w + 1);
+    const long long sl = l1[(size_t)i * W + j], sll = l2[(size_t)i * W + j];
+    const double sdl = sqrt((double)(n * sll - sl * sl));
+    double run = 0.0;  // running maximum over the chunks already processed
+    bool have = false, nan0 = false;
+    int best = 0;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        const int d = d0 + lane;
+        double c = -INFINITY;
+        bool isnan_c = false;
+        if (d < D) {
+            const int raw = slr[q * D + d];
+            if (raw < 0) {
+                c = 255.0;
+            } else {
+                const long long sr = r1[(size_t)i * W + j - d], srr = r2[(size_t)i * W + j - d];
+                const double num = (double)(n * (long long)raw - sl * sr);
+                c = num / (sdl * sqrt((double)(n * srr - sr * sr)));
+                if (c != c) {
+                    isnan_c = true;
+                    c = -INFINITY;  // a NaN never compares greater (NCC.h:59) and never raises the maximum
+                }
+            }
+        }
+        if (d0 == 0) nan0 = __shfl_sync(0xffffffffu, (int)isnan_c, 0) != 0;
+        // exclusive prefix maximum inside the chunk, seeded with the running maximum
+        double incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = fmax(incl, up);
+        }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = -INFINITY;
+        const bool seeded = have || lane > 0;
+        if (have) excl = fmax(excl, run);
+        const bool acc = d < D && d >= 1 && seeded && !isnan_c && c > (double)(float)excl;
+        const unsigned m = __ballot_sync(0xffffffffu, acc);
+        if (m) best = d0 + 31 - __clz(m);
+        const double cm = __shfl_sync(0xffffffffu, incl, 31);
+        run = have ? fmax(run, cm) : cm;
+        have = true;
+    }
+    if (nan0) best = 0;  // m = NaN from the start: no later disparity is ever accepted
+    if (lane == 0) disp[(size_t)i * W + j] = best;
+}
+
+// ---------------------------------------------------------------------------------------------- ASW
+constexpr int ASW_TX = 4, ASW_TD = 64;
+
+// Lp/Rp: replicate-padded grey [Hp][Wp], pad = wins = winSize+1 (ASWeight.cpp:54-55).  One block per (output row,
+// ASW_TX columns); thread = (column, disparity lane).  cost = sum(wOwn*wOth*min(|a-b|,T)) / sum(wOwn*wOth) with
+// w = colour[|p - centre|] * space[tap] (ASW.h:210-257); first-minimum WTA (:193-208).
+__global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __restrict__ own_img, const uint8_t* __restrict__ oth_img,
+                                                              int Hp, int Wp, int wins, int D, int T, int right_view,
+                                                              const float* __restrict__ space, const float* __restrict__ color,
+                                                              float* __restrict__ disp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = 2 * wins + 1, kk = k * k;
+    const int Wo = Wp - 2 * wins;
+    const int own_w = ASW_TX + k - 1, oth_w = ASW_TX + k - 1 + D - 1;
+    float* s_space = reinterpret_cast<float*>(smem_raw);       // [kk]
+    float* s_color = s_space + kk;                             // [256]
+    float* s_wown = s_color + 256;                             // [ASW_TX][kk]
+    float* s_bestv = s_wown + ASW_TX * kk;                     // [ASW_TX][ASW_TD]
+    int* s_bestd = reinterpret_cast<int*>(s_bestv + ASW_TX * ASW_TD);
+    uint8_t* s_own = reinterpret_cast<uint8_t*>(s_bestd + ASW_TX * ASW_TD);  // [k][own_w]
+    uint8_t* s_oth = s_own + (size_t)k * own_w;                             // [k][oth_w]
+
+    const int io = blockIdx.y, jo0 = blockIdx.x * ASW_TX;
+    const int tid = threadIdx.x, xl = tid / ASW_TD, dl = tid % ASW_TD;
+    const int oth_base = right_view ? jo0 : jo0 - (D - 1);  // padded column of s_oth[.][0]
+    for (int t = tid; t < kk; t += blockDim.x) s_space[t] = space[t];
+    for (int t = tid; t < 256; t += blockDim.x) s_color[t] = color[t];
+    for (int t = tid; t < k * own_w; t += blockDim.x) {
+        const int r = t / own_w, c = t - r * own_w;
+        const int x = jo0 + c;
+        s_own[t] = x < Wp ? own_img[(size_t)(io + r) * Wp + x] : 0;
+    }
+    for (int t = tid; t < k * oth_w; t += blockDim.x) {
+        const int r = t / oth_w, c = t - r * oth_w;
+        const int x = oth_base + c;
+        s_oth[t] = (x >= 0 && x < Wp) ? oth_img[(size_t)(io + r) * Wp + x] : 0;
+    }
+    __syncthreads();
+    // weight table of each reference pixel: colour[|p - centre|] * space
+    for (int t = tid; t < ASW_TX * kk; t += blockDim.x) {
+        const int x = t / kk, tap = t - x * kk;
+        const int r = tap / k, c = tap - r * k;
+        const int centre = s_own[(size_t)wins * own_w + x + wins];
+        s_wown[t] = __fmul_rn(s_color[abs((int)s_own[(size_t)r * own_w + x + c] - centre)], s_space[tap]);
+    }
+    __syncthreads();
+
+    const int jo = jo0 + xl;
+    float bestv = INFINITY;
+    int bestd = 0x7fffffff;
+    for (int d = dl; d < D; d += ASW_TD) {
+        const bool valid = right_view ? (jo + d < Wo - wins - 1) : (jo - d >= 0);
+        if (jo >= Wo || !valid) continue;
+        const int off = right_view ? xl + d : xl + (D - 1 - d);  // column of the other window's left edge in s_oth
+        const int cb = s_oth[(size_t)wins * oth_w + off + wins];
+        const float* wo = s_wown + xl * kk;
+        float sw = 0.f, sv = 0.f;
+        for (int r = 0; r < k; ++r) {
+            const uint8_t* a = s_own + (size_t)r * own_w + xl;
+            const uint8_t* b = s_oth + (size_t)r * oth_w + off;
+            const float* sp = s_space + r * k;
+            const float* w0 = wo + r * k;
+            for (int c = 0; c < k; ++c) {
+                const int pa = a[c], pb = b[c];
+                const float m1 = __fmul_rn(s_color[abs(pb - cb)], sp[c]);
+                const float m2 = __fmul_rn(w0[c], m1);
+                const int e = min(abs(pa - pb), T);
+                sw = __fadd_rn(sw, m2);
+                sv = __fadd_rn(sv, __fmul_rn(m2, (float)e));
+            }
+        }
+        const float cost = __fdiv_rn(sv, sw);
+        if (cost < bestv) {  // ascending d inside the thread: strict '<' keeps the first minimum
+            bestv = cost;
+            bestd = d;
+        }
+    }
+    s_bestv[tid] = bestv;
+    s_bestd[tid] = bestd;
+    __syncthreads();
+    if (dl == 0 && jo < Wo) {
+        float bv = INFINITY;
+        int bd = 0x7fffffff;
+        for (int t = 0; t < ASW_TD; ++t) {
+            const float v = s_bestv[xl * ASW_TD + t];
+            const int dd = s_bestd[xl * ASW_TD + t];
+            if (dd != 0x7fffffff && (v < bv || (v == bv && dd < bd))) {
+                bv = v;
+                bd = dd;
+            }
+        }
+        disp[(size_t)io * Wo + jo] = bd == 0x7fffffff ? 0.f : (float)bd;
+    }
+}
+
+// CrossCheckDiaparity (ASW.h:108-145)
+__global__ void __launch_bounds__(256) asw_crosscheck_kernel(const float* __restrict__ dl, const float* __restrict__ dr, int H, int W,
+                                                             uint8_t* __restrict__ out) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (size_t)H * W) return;
+    const int j = (int)(p % W);
+    const int lv = (int)dl[p];
+    const int jj = min(max(j - lv, 0), W - 1);  // the reference indexes j - lv unchecked; left disparities satisfy lv <= j
+    const float rv = dr[p - j + jj];
+    out[p] = fabsf((float)lv - rv) > 5.f ? 0 : (uint8_t)lv;
+}
+
+// ---------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded, int32_t cols_padded,
+                     int32_t D, int32_t winsize, int32_t right_view, int32_t* disp, float* costs, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    const int w = winsize + 1;
+    SMT_REQUIRE(ctx, left_padded && right_padded && disp && D > 0 && winsize >= 0 && rows_padded > 2 * w && cols_padded > 2 * w,
+                SMT_ERR_INVALID_ARG, "smt_sad: bad argument");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int Ho = rows_padded - 2 * w, Wo = cols_padded - 2 * w;
+    const size_t np = (size_t)rows_padded * cols_padded, no = (size_t)Ho * Wo;
+    Marshal ms(ctx, space);
+    const uint8_t* dl = ms.in(left_padded, np);
+    const uint8_t* dr = ms.in(right_padded, np);
+    int32_t* dd = ms.out(disp, no);
+    float* dc = ms.out(costs, no * D);
+    SMT_TRY(ms.check());
+    SMT_ALLOC(ctx, vol, no * D * sizeof(int));
+    {
+        StageTimer t(ctx, ST_COST);
+        if (!right_view)
+            SMT_TRY(k_box_sum(ctx, 0, dl, dr, rows_padded, cols_padded, w, -1, D, vol.as<int>()));
+        else
+            SMT_TRY(k_box_sum(ctx, 0, dr, dl, rows_padded, cols_padded, w, +1, D, vol.as<int>()));
+    }
+    {
+        StageTimer t(ctx, ST_WTA);
+        SMT_LAUNCH(ctx, sad_select_kernel, cdiv((long long)no, 128), 128, 0, vol.as<int>(), Ho, Wo, D, right_view ? 1 : 0, dd, dc);
+    }
+    return ms.finish();
+}
+
+smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols, int32_t win_size, int32_t D,
+                     int32_t* disp, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    const int w = win_size;
+    SMT_REQUIRE(ctx, left && right && disp && D > 0 && w >= 0 && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_ncc: bad argument");
+    SMT_REQUIRE(ctx, (long long)(2 * w + 1) * (2 * w + 1) * 65025 < 2147483647ll, SMT_ERR_UNSUPPORTED,
+                "smt_ncc: window too large for 32-bit window sums");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t np = (size_t)rows * cols;
+    Marshal ms(ctx, space);
+    const uint8_t* dl = ms.in(left, np);
+    const uint8_t* dr = ms.in(right, np);
+    int32_t* dd = ms.out(disp, np);
+    SMT_TRY(ms.check());
+    SMT_CUDA(ctx, cudaMemsetAsync(dd, 0, np * sizeof(int32_t), ctx->stream));  // borders stay 0 (NCC_main.cpp:20)
+    if (rows > 2 * w && cols > 2 * w) {
+        const int Ho = rows - 2 * w, Wo = cols - 2 * w;
+        SMT_ALLOC(ctx, stats, 4 * np * sizeof(int));
+        SMT_ALLOC(ctx, vol, (size_t)Ho * Wo * D * sizeof(int));
+        int* s = stats.as<int>();
+        {
+            StageTimer t(ctx, ST_COST);
+            dim3 g(cdiv(cols, 128), rows);
+            SMT_LAUNCH(ctx, ncc_stats_kernel, g, 128, 0, dl, rows, cols, w, s, s + np);
+            SMT_LAUNCH(ctx, ncc_stats_kernel, g, 128, 0, dr, rows, cols, w, s + 2 * np, s + 3 * np);
+            SMT_TRY(k_box_sum(ctx, 1, dl, dr, rows, cols, w, -1, D, vol.as<int>()));
+        }
+        {
+            StageTimer t(ctx, ST_WTA);
+            SMT_LAUNCH(ctx, ncc_select_kernel, cdiv((long long)Ho * Wo, 8), 256, 0, vol.as<int>(), s, s + np, s + 2 * np, s + 3 * np, rows,
+                       cols, w, D, dd);
+        }
+    }
+    return ms.finish();
+}
+
+smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded, int32_t cols_padded,
+                     int32_t win_size, int32_t D, double space_sigma, double color_sigma, int32_t T, int32_t right_view, float* disp,
+                     smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    const int wins = win_size + 1, k = 2 * wins + 1;
+    SMT_REQUIRE(ctx, left_padded && right_padded && disp && D > 0 && win_size >= 0 && rows_padded > 2 * wins && cols_padded > 2 * wins,
+                SMT_ERR_INVALID_ARG, "smt_asw: bad argument");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int Ho = rows_padded - 2 * wins, Wo = cols_padded - 2 * wins;
+    const size_t np = (size_t)rows_padded * cols_padded, no = (size_t)Ho * Wo;
+    const size_t smem = sizeof(float) * ((size_t)k * k + 256 + (size_t)ASW_TX * k * k + ASW_TX * ASW_TD) + sizeof(int) * ASW_TX * ASW_TD +
+                        (size_t)k * (ASW_TX + k - 1) + (size_t)k * (ASW_TX + k - 1 + D - 1);
+    SMT_REQUIRE(ctx, smem <= 200 * 1024, SMT_ERR_UNSUPPORTED, "smt_asw: window / disparity range too large for the shared-memory tile");
+    Marshal ms(ctx, space);
+    const uint8_t* dl = ms.in(left_padded, np);
+    const uint8_t* dr = ms.in(right_padded, np);
+    float* dd = ms.out(disp, no);
+    SMT_TRY(ms.check());
+    // masks evaluated on the host in double like the reference (ASW.h:16-47), used as float weights on the device
+    std::vector<float> h((size_t)k * k + 256);
+    const int c = (k - 1) / 2;
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j)
+            h[(size_t)i * k + j] = (float)std::exp(-(std::pow(j - c, 2) + std::pow(i - c, 2)) / (2 * space_sigma * space_sigma));
+    for (int i = 0; i < 256; ++i) h[(size_t)k * k + i] = (float)std::exp(-(i * i) / (2 * color_sigma * color_sigma));
+    SMT_ALLOC(ctx, masks, h.size() * sizeof(float));
+    SMT_CUDA(ctx, cudaMemcpyAsync(masks.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h is a local vector
+    if (smem > 48 * 1024) SMT_CUDA(ctx, cudaFuncSetAttribute(asw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        StageTimer t(ctx, ST_COST);
+        dim3 grid(cdiv(Wo, ASW_TX), Ho);
+        SMT_LAUNCH(ctx, asw_kernel, grid, ASW_TX * ASW_TD, smem, right_view ? dr : dl, right_view ? dl : dr, rows_padded, cols_padded, wins, D,
+                   T, right_view ? 1 : 0, masks.as<float>(), masks.as<float>() + (size_t)k * k, dd);
+    }
+    return ms.finish();
+}
+
+smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, const float* disp_right, int32_t rows, int32_t cols, uint8_t* out,
+                                smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, disp_left && disp_right && out && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_asw_crosscheck: bad argument");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)rows * cols;
+    Marshal ms(ctx, space);
+    const float* dl = ms.in(disp_left, n);
+    const float* dr = ms.in(disp_right, n);
+    uint8_t* dout = ms.out(out, n);
+    SMT_TRY(ms.check());
+    {
+        StageTimer t(ctx, ST_POST);
+        SMT_LAUNCH(ctx, asw_crosscheck_kernel, cdiv((long long)n, 256), 256, 0, dl, dr, rows, cols, dout);
+    }
+    return ms.finish();
+}
+
+}  // extern "C"

@@ -59,13 +59,24 @@ def test_crossarm_aggregation(engine, oracle, H, W, D, kind, seed):
 
 
 def test_flat_index_out_of_bounds_is_refused(engine, oracle):
-    H, W, D = 48, 80, 2   # floor((H*H-1)/W)+34 >= H-1: the reference reads past the buffer here
-    p = make_pair(H, W, D, 3, "scene")
-    arms = engine.arms_gray(p["gray_left"], 30, variant=0)
+    """The scrambled Right map can push the flat index past the slice; the engine checks the actual
+    addresses and refuses instead of reading out of bounds like the reference."""
+    H, W, D = 12, 20, 2
+    z = np.zeros((H, W), np.int32)
+    right = z.copy()
+    right[H - 1, W - 1] = 3          # (H-1)*W + (W-1) + 3 >= H*W
     vol = np.ones((H, W, D), np.float32)
-    with pytest.raises(SmtError) as e:
-        engine.aggregate_rect(vol, arms["left"], arms["right"], arms["top"], arms["bottom"], variant=0)
-    assert e.value.status == 2
+    for variant in (0, 2):
+        with pytest.raises(SmtError) as e:
+            engine.aggregate_rect(vol, z, right, z, z, variant=variant)
+        assert e.value.status == 2
+    # the same window one row up only wraps into the next row: allowed for the flat variants, refused for V5
+    right = z.copy()
+    right[H - 2, W - 1] = 3
+    out = engine.aggregate_rect(vol, z, right, z, z, variant=0)
+    assert np.all(out == 1)
+    with pytest.raises(SmtError):
+        engine.aggregate_rect(vol, z, right, z, z, variant=2)
 
 
 @pytest.mark.parametrize("H,W,D,kind,seed", ANY)

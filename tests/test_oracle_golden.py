@@ -45,3 +45,36 @@ def test_first_min_tie_break_and_constant_image(oracle_port):
     vol[..., 3] = 0.5
     vol[..., 6] = 0.5
     assert np.all(oracle_port.wta(vol) == 3)
+
+
+# ---------------------------------------------------------------------------------------------- matchers / CrossArm / CBLSM
+from oracle.make_golden_matchers import CROSSARM_CASES, MATCHER_CASES, crossarm_outputs, matcher_outputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", MATCHER_CASES, ids=[c[0] for c in MATCHER_CASES])
+def test_port_matchers_reproduce_reference_golden(oracle_port, case):
+    name = case[0]
+    out = matcher_outputs(oracle_port, *case[1:])
+    for k, v in out.items():
+        assert digest(v) == DIGESTS[name]["outputs"][k], f"{name}:{k}"
+    f = GOLDEN / f"{name}.npz"
+    if f.exists():
+        z = np.load(f)
+        for k, v in out.items():
+            assert np.array_equal(v, z[k]), f"{name}:{k}"
+
+
+@pytest.mark.parametrize("case", CROSSARM_CASES, ids=[c[0] for c in CROSSARM_CASES])
+def test_port_crossarm_cblsm_reproduce_reference_golden(oracle_port, case):
+    name = case[0]
+    out = crossarm_outputs(oracle_port, *case[1:])
+    for k, v in out.items():
+        assert digest(v) == DIGESTS[name]["outputs"][k], f"{name}:{k}"
+
+
+def test_sad_optimal_disparity_quirks(oracle_port):
+    """Sad.h:40-85: the search starts at d=1, d=0 wins ties, the last disparity is rejected."""
+    assert oracle_port.sad_optimal_disparity(np.array([5, 9, 3, 7], np.float32)) == 2
+    assert oracle_port.sad_optimal_disparity(np.array([3, 9, 3, 7], np.float32)) == 0      # sad[0] <= min
+    assert oracle_port.sad_optimal_disparity(np.array([5, 9, 7, 3], np.float32)) == 0      # best == D-1
+    assert oracle_port.sad_optimal_disparity(np.array([9, 4, 4, 7], np.float32)) == 1      # first minimum
