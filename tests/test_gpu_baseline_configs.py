@@ -1,0 +1,108 @@
+"""GPU parity at the shapes BASELINE.json names (configs[0..3]); the oracle runs on the box's CPU, so full frames are
+used where it finishes in seconds and row bands / size-independent properties where it does not."""
+import numpy as np
+import pytest
+
+from stereo_match_traditional_b200.api import SUM_FAST, SUM_REFERENCE_ORDER
+from stereo_match_traditional_b200.synth import make_pair, replicate_pad
+from conftest import rel_err
+from test_gpu_adcensus_path import oracle_pfull
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_pfull_teddy_shape(engine, oracle):
+    """configs[1]: AD-Census full pipeline at 450x375, D=64 against the reference CPU path."""
+    H, W, D = 375, 450, 64
+    p = make_pair(H, W, D, 1002, "scene")
+    ref = oracle_pfull(oracle, p, D)
+    names = ("disp", "left_raw", "right_raw", "lrc")
+    got = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=names,
+                          sum_mode=SUM_REFERENCE_ORDER)
+    for n in names:
+        assert np.array_equal(got[n], ref[n]), n
+    fast = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=names, sum_mode=SUM_FAST)
+    for n in ("left_raw", "right_raw", "disp"):
+        same = (fast[n] == ref[n]).mean()
+        assert same >= 0.999, f"{n}: {same:.4%}"
+    assert np.abs(fast["left_raw"] - ref["left_raw"]).max() <= 1 and np.abs(fast["right_raw"] - ref["right_raw"]).max() <= 1
+
+
+def test_config4_full_hd_fast_vs_reference_order(engine):
+    """configs[3] shape, 1920x1080 D=256: the reference-order kernels (bit-exact with the reference at every shape the
+    oracle can run) are the yardstick for the fast path at full size."""
+    import torch
+
+    H, W, D = 1080, 1920, 256
+    p = make_pair(H, W, D, 1004, "scene")
+    dev = "cuda:0"
+    t = {k: torch.as_tensor(p[k], device=dev) for k in ("bgr_left", "bgr_right", "gray_left", "gray_right")}
+    gl = t["gray_left"].float()
+    gr = t["gray_right"].float()
+    cost = engine.adcensus_cost(gl, gr, D)["cost"]
+    exact = engine.aggregate_cross(t["bgr_left"], cost, mode=SUM_REFERENCE_ORDER)["cost"]
+    fast = engine.aggregate_cross(t["bgr_left"], cost, mode=SUM_FAST)["cost"]
+    del cost
+    rel = ((fast - exact).abs() / exact.abs().clamp_min(1e-30))
+    rel[fast == exact] = 0
+    assert float(rel.max()) <= 1e-5, f"max rel err {float(rel.max()):.3e}"
+    del rel, exact, fast
+    torch.cuda.empty_cache()
+    names = ("disp", "left_raw", "right_raw")
+    a = engine.pipeline(t["bgr_left"], t["bgr_right"], D, t["gray_left"], t["gray_right"], want=names, sum_mode=SUM_REFERENCE_ORDER)
+    b = engine.pipeline(t["bgr_left"], t["bgr_right"], D, t["gray_left"], t["gray_right"], want=names, sum_mode=SUM_FAST)
+    for n in names:
+        same = float((a[n] == b[n]).float().mean())
+        assert same >= 0.999, f"{n}: {same:.4%}"
+    assert float((a["left_raw"] - b["left_raw"]).abs().max()) <= 1
+    # planted disparities: background round(0.08*D)=20, rectangle round(0.17*D)=44 dominate the valid pixels
+    d = b["disp"].cpu().numpy()
+    gt = p["disp_gt"]
+    ok = np.isfinite(d) & (d < 1e9)
+    assert (np.abs(d[ok] - gt[ok]) <= 1).mean() > 0.9
+
+
+def test_config3_ncc_asw_hd_band(engine, oracle):
+    """configs[2]: NCC and ASW at 1280x720, D=128 -- full frame on the GPU, a row band against the oracle."""
+    H, W, D = 720, 1280, 128
+    p = make_pair(H, W, D, 1003, "scene")
+    gl, gr = p["gray_left"], p["gray_right"]
+    # NCC, winSize 10 (21x21, NCC_main.cpp:17): rows 300..303 need image rows 290..313
+    w = 10
+    got = engine.ncc(gl, gr, D, w)
+    r0, nr = 300, 4
+    band = oracle.ncc(gl[r0 - w:r0 + nr + w], gr[r0 - w:r0 + nr + w], D, w)
+    same = (got[r0:r0 + nr] == band[w:w + nr]).mean()
+    assert same >= 0.999, f"NCC band: {same:.4%}"
+    # ASW, winSize 11 (25x25, ASWeight.cpp:43): two output rows
+    win = 11
+    lp, rp = replicate_pad(gl, win + 1), replicate_pad(gr, win + 1)
+    ga = engine.asw(lp, rp, D, win, 50, 30, 40)
+    nr = 2
+    ba = oracle.asw(lp[r0:r0 + nr + 2 * (win + 1)], rp[r0:r0 + nr + 2 * (win + 1)], D, win, 50, 30, 40)
+    same = (ga[r0:r0 + nr] == ba).mean()
+    assert same >= 0.999, f"ASW band: {same:.4%}"
+
+
+def test_cpp_facade_runs_reference_call_order(engine, oracle, tmp_path):
+    """include/smt_b200.hpp driven like AD-CensusV1/main.cpp (tests/cpp/facade_main.cpp) == the pipeline == the oracle."""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(__file__).resolve().parent / "cpp" / "facade_main"
+    if not exe.exists():
+        pytest.skip("tests/cpp/facade_main not built (make -C stereo_match_traditional_b200/csrc facade)")
+    H, W, D = 48, 160, 24
+    p = make_pair(H, W, D, 77, "scene")
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(np.array([H, W, D], np.int32).tobytes())
+        for k in ("gray_left", "gray_right", "bgr_left", "bgr_right"):
+            f.write(np.ascontiguousarray(p[k]).tobytes())
+    r = subprocess.run([str(exe), str(fin), str(fout)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(fout, np.float32).reshape(3, H, W)
+    ref = oracle_pfull(oracle, p, D)
+    assert np.array_equal(out[0], ref["disp"])
+    assert np.array_equal(out[1], ref["left_raw"])
+    assert np.array_equal(out[2], ref["right_raw"])
