@@ -183,6 +183,7 @@ def gpu_arm(args, H, W, D):
     import torch.distributed as dist
 
     from stereo_match_traditional_b200.api import SUM_FAST, SUM_REFERENCE_ORDER, Engine
+    from stereo_match_traditional_b200.stream import aggregate_fps, frame_seed, frames_for_rank, reduce_max
     from stereo_match_traditional_b200.synth import make_pair
 
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +197,7 @@ def gpu_arm(args, H, W, D):
     mode = SUM_FAST if args.sum_mode == "fast" else SUM_REFERENCE_ORDER
 
     # distinct frames per rank and per slot (seed 1004 + frame)
-    frames = [make_pair(H, W, D, 1004 + rank * B + f, "scene", frame=rank * B + f) for f in range(B)]
+    frames = [make_pair(H, W, D, frame_seed(f), "scene", frame=f) for f in frames_for_rank(rank, world, B)]
     keys = ("bgr_left", "bgr_right", "gray_left", "gray_right")
     dev_frames = [{k: torch.as_tensor(fr[k], device=dev) for k in keys} for fr in frames]
     pin_frames = [{k: torch.as_tensor(fr[k]).pin_memory() for k in keys} for fr in frames]
@@ -235,10 +236,7 @@ def gpu_arm(args, H, W, D):
                 fn()
             e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return reduce_max(e0.elapsed_time(e1), dev)
 
     for _ in range(args.warmup):
         step_device()
@@ -247,12 +245,12 @@ def gpu_arm(args, H, W, D):
     with ClockSampler(local) as clk:
         ms = timed(step_device, args.steps)
     launches = eng.kernel_launches - l0
-    fps = world * B * args.steps / (ms / 1e3)
+    fps = aggregate_fps(world, B, args.steps, ms)
 
     # end-to-end through the host-memspace ABI (pinned host buffers, copies inside the timed region)
     step_host()
     ms_e2e = timed(step_host, args.steps)
-    fps_e2e = world * B * args.steps / (ms_e2e / 1e3)
+    fps_e2e = aggregate_fps(world, B, args.steps, ms_e2e)
 
     # per-stage CUDA-event times for the roofline of the dominant kernel
     eng.stage_timing(True)
