@@ -221,6 +221,9 @@ struct Pass {
 
 }  // namespace
 
+smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
+                            int horiz, bool nonneg, float bias);  // cross_agg_seq.cu
+
 // vmax: an upper bound of the (non-negative) input values, or <= 0 when the sign/range of the input is unknown.
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
                                     const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result) {
@@ -250,6 +253,19 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
     while (nonneg && b_plain < vmax) b_plain *= 2.f;
     const float b_sum = b_plain * 128.f;  // input of a dividing pass: sums of <= 69 such values
     static const bool fuse_pairs = getenv("SMT_AGG_NO_FUSE") == nullptr;
+    // default: the streaming one-warp-per-line kernel (cross_agg_seq.cu); SMT_AGG_KERNEL=tile selects the tiled one
+    static const bool use_tile = getenv("SMT_AGG_KERNEL") != nullptr && std::string(getenv("SMT_AGG_KERNEL")) == "tile";
+    if (!use_tile) {
+        for (size_t k = 0; k < passes.size(); ++k) {
+            SMT_TRY(k_agg_seq_pass(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg,
+                                   passes[k].sup ? b_sum : b_plain));
+            float* sw = cur;
+            cur = oth;
+            oth = sw;
+        }
+        *result = cur;
+        return SMT_OK;
+    }
     for (size_t k = 0; k < passes.size();) {
         const bool fuse = fuse_pairs && k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz;
         // input of pass k is a plain cost if pass k does not divide (it is the first pass of its iteration)

@@ -1,0 +1,205 @@
+// SMT_SUM_FAST cross aggregation, streaming form: one warp walks one whole line.
+//
+// A pass along a line is out[j] = E[j+hi(j)+1] - E[j-lo(j)] with E the exclusive prefix of the line and lo, hi <= 34
+// the pixel's arms (cross_aggregator.cpp:353-389).  Because the arms are bounded, an output only ever needs prefix
+// entries within [j-34, j+35]: a warp walks the line ONCE, keeps the running compensated prefix in registers and the
+// last 96 entries in a shared-memory ring, and emits output j as soon as the prefix has reached j+35.
+//   * lane = disparity: every load / store is a 128-byte row of the [H][W][D] volume; arms, support counts and ring
+//     slots are warp-uniform, prepared 32 positions at a time (one per lane) and read back as broadcast LDS;
+//   * no tiles: no halo re-reads, no segment totals, no block barriers -- the ring is lane-private storage;
+//   * the ring has 96 = 3*32 slots and chunks are 32 positions, so inside a chunk every ring store has a compile-time
+//     offset; the interior chunks of a line run a predicate-free path;
+//   * per cell: 4 FADD (prefix) + 3 FADD (difference) + 3 FMA-class ops for the exact division + 1 STS.64 + 3 LDS + 1 LDG +
+//     1 STG + ~6 integer ops, against ~65 instructions for the tiled kernel in cross_agg_fast.cu;
+//   * input rows are prefetched a full chunk (4 KB per warp) ahead into a second register buffer.
+// Numerics are those of cross_agg_fast.cu: cascaded compensated prefix (s, c) for non-negative input (a power-of-two
+// bias keeps the FastTwoSum error term exact), general TwoSum pair otherwise; window sums are exact to ~2^-46 and
+// rounded once.  The division by the support count is the correctly rounded quotient (Markstein's residual step on the
+// correctly rounded reciprocal), i.e. the same bits as the reference's IEEE `cost / count` (:389).
+#include "common.cuh"
+
+namespace {
+
+constexpr int SEQ_R = 96;     // ring entries: three chunks
+constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
+constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
+
+struct pair2 {
+    float a, b;
+};
+template <bool NONNEG>
+__device__ __forceinline__ pair2 pre_add(pair2 p, float v) {
+    pair2 r;
+    if (NONNEG) {  // (s, c): value s + c, FastTwoSum (|s| >= |v| thanks to the bias)
+        r.a = __fadd_rn(p.a, v);
+        r.b = __fadd_rn(p.b, __fsub_rn(v, __fsub_rn(r.a, p.a)));
+    } else {  // (hi, lo): TwoSum + renormalisation
+        const float s = __fadd_rn(p.a, v);
+        const float bb = __fsub_rn(s, p.a);
+        const float e = __fadd_rn(__fsub_rn(p.a, __fsub_rn(s, bb)), __fsub_rn(v, bb));
+        const float l = __fadd_rn(p.b, e);
+        r.a = __fadd_rn(s, l);
+        r.b = __fsub_rn(l, __fsub_rn(r.a, s));
+    }
+    return r;
+}
+
+// correctly rounded a / b for b = a support count (integer 1..4761) given y = RN(1/b)
+__device__ __forceinline__ float div_by_count(float a, float b, float y) {
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
+// window descriptor of one output position: byte offsets of E[j-lo] and E[j+hi+1] in the lane's ring column, the
+// support count as float and its reciprocal
+struct __align__(16) Desc {
+    unsigned offa, offb;
+    float cnt, rcp;
+};
+
+// One chunk of 32 positions starting at tb (a multiple of 32).  Loads chunk tb+32 into `vload`, consumes `vuse`
+// (chunk tb): 32 prefix steps (E[tb+k] is stored BEFORE v[tb+k] is added, so slots never wrap inside a chunk), and
+// after every 8 of them the 8 outputs j = tb+kk-35 that have become computable.  EDGE adds the range predicates.
+template <bool NONNEG, bool HAS_SUP, bool EDGE>
+__device__ __forceinline__ void seq_chunk(pair2& acc, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
+                                          const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
+                                          long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
+                                          const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane) {
+    // ---- loads of the next chunk (consumed one chunk later)
+    {
+        const float* p = src_next;
+#pragma unroll
+        for (int k = 0; k < SEQ_CH; ++k) {
+            if (EDGE)
+                vload[k] = (tb + SEQ_CH + k < len && act) ? __ldg(p) : 0.f;
+            else
+                vload[k] = __ldg(p);
+            p += step;
+        }
+    }
+    // ---- descriptors of the outputs of this chunk: position tb - 35 + lane
+    {
+        const int j = tb - SEQ_LOOK + lane;
+        Desc ds{0u, 0u, 1.f, 1.f};
+        if (!EDGE || (j >= 0 && j < len)) {
+            const long long pix = pbase + pstride * j;
+            const uchar4 a = __ldg(arms + pix);
+            const int lo = horiz ? a.x : a.z, hi = horiz ? a.y : a.w;
+            const int sa = (j - lo) % SEQ_R, sb = (j + hi + 1) % SEQ_R;  // j - lo >= 0: arms stop at the image border
+            ds.offa = (unsigned)sa * 256u;
+            ds.offb = (unsigned)sb * 256u;
+            if (HAS_SUP) {
+                ds.cnt = (float)(int)__ldg(sup + pix);
+                ds.rcp = __frcp_rn(ds.cnt);
+            }
+        }
+        __syncwarp();  // the previous chunk's descriptor reads are done
+        desc[lane] = ds;
+        __syncwarp();
+    }
+    unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;  // slot of E[tb]
+    float* dp = dst_first;                                             // output position tb - 35
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) {
+        *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E[tb+k]
+        acc = pre_add<NONNEG>(acc, vuse[k]);
+        if ((k & 7) == 7) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kk = k - 7 + u;
+                const Desc ds = desc[kk];  // broadcast
+                if (!EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len)) {
+                    const float2 ea = *reinterpret_cast<const float2*>(ring_col + ds.offa);
+                    const float2 eb = *reinterpret_cast<const float2*>(ring_col + ds.offb);
+                    float r = __fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y));
+                    if (HAS_SUP) r = div_by_count(r, ds.cnt, ds.rcp);
+                    if (!EDGE || act) *dp = r;
+                }
+                dp += step;
+            }
+        }
+    }
+}
+
+template <bool NONNEG, bool HAS_SUP>
+__global__ void __launch_bounds__(32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                     const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
+                                                     int D, int horiz, float bias) {
+    __shared__ __align__(16) unsigned char s_ring[SEQ_R * 256];  // [slot][lane] float2
+    __shared__ Desc s_desc[SEQ_CH];
+    const int lane = threadIdx.x;
+    const int nchunk = (D + 31) >> 5;
+    const long long wg = blockIdx.x;
+    const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
+    const int len = horiz ? W : H;
+    const int d = chunk * 32 + lane;
+    const bool act = d < D;
+    const bool full = chunk * 32 + 32 <= D;  // every lane active: the interior path needs no lane predicate
+    const long long pstride = horiz ? 1 : (long long)W;
+    const long long pbase = horiz ? (long long)line * W : (long long)line;
+    const long long step = pstride * D;
+    const float* src = in + pbase * D + (act ? d : 0);
+    float* dst = out + pbase * D + (act ? d : 0);
+    unsigned char* ring_col = s_ring + lane * 8;
+
+    pair2 acc{NONNEG ? bias : 0.f, 0.f};
+    float va[SEQ_CH], vb[SEQ_CH];  // two register buffers: a chunk's loads stay in flight for a whole chunk
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) va[k] = (k < len && act) ? __ldg(src + step * k) : 0.f;
+
+    // chunk ob covers prefix positions [32*ob, 32*ob+32) and outputs [32*ob-35, 32*ob-3); outputs end at len-1
+    const int nouter = (len + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;
+    for (int ob = 0; ob < nouter; ob += 2) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int o = ob + half;
+            if (o >= nouter) break;
+            const int tb = o * SEQ_CH;
+            const float* src_next = src + step * (tb + SEQ_CH);
+            float* dst_first = dst + step * (tb - SEQ_LOOK);
+            // interior: next chunk fully inside the line, all outputs of this chunk inside the line, all lanes active
+            const bool interior = full && tb - SEQ_LOOK >= 0 && tb + 2 * SEQ_CH <= len;
+            if (half == 0) {
+                if (interior)
+                    seq_chunk<NONNEG, HAS_SUP, false>(acc, va, vb, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms,
+                                                      sup, ring_col, s_desc, lane);
+                else
+                    seq_chunk<NONNEG, HAS_SUP, true>(acc, va, vb, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms, sup,
+                                                     ring_col, s_desc, lane);
+            } else {
+                if (interior)
+                    seq_chunk<NONNEG, HAS_SUP, false>(acc, vb, va, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms,
+                                                      sup, ring_col, s_desc, lane);
+                else
+                    seq_chunk<NONNEG, HAS_SUP, true>(acc, vb, va, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms, sup,
+                                                     ring_col, s_desc, lane);
+            }
+        }
+    }
+}
+
+template <bool NONNEG, bool HAS_SUP>
+static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
+                               int horiz, float bias) {
+    static bool attr_set = false;
+    if (!attr_set) {  // ~25 KB of static shared memory per one-warp block: ask for the largest carveout (9 blocks / SM)
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP>), (unsigned)nwarps, 32, 0, in, out, arms, sup, H, W, D, horiz, bias);
+    return SMT_OK;
+}
+
+}  // namespace
+
+smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
+                            int horiz, bool nonneg, float bias) {
+    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    if (nonneg)
+        return sup ? launch_seq<true, true>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
+                   : launch_seq<true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+    return sup ? launch_seq<false, true>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
+               : launch_seq<false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+}
