@@ -262,7 +262,7 @@ def gpu_arm(args, H, W, D):
     V = 4.0 * H * W * D
     iters = params.agg_iters
     alg = {"cost": 2 * V, "aggregate": 2 * V * iters * 2, "scanline": 2 * V, "wta": 1 * V}   # SURVEY.md 8(d), both views
-    kern = {"cost": "adcensus_cost_kernel", "aggregate": "agg_line_kernel" if mode == SUM_FAST else "agg_pass_exact_kernel",
+    kern = {"cost": "adcensus_cost_kernel", "aggregate": "agg_seq_kernel" if mode == SUM_FAST else "agg_pass_exact_kernel",
             "scanline": "scan_path_kernel", "wta": "wta_first_min_kernel"}
     dom = max(alg, key=lambda k: st.get(k, 0.0))
     peak, how = measured_hbm_peak()

@@ -61,38 +61,52 @@ struct __align__(16) Desc {
 // One chunk of 32 positions starting at tb (a multiple of 32).  Loads chunk tb+32 into `vload`, consumes `vuse`
 // (chunk tb): 32 prefix steps (E[tb+k] is stored BEFORE v[tb+k] is added, so slots never wrap inside a chunk), and
 // after every 8 of them the 8 outputs j = tb+kk-35 that have become computable.  EDGE adds the range predicates.
+struct Prefetched {  // arm word (lo | hi << 8) and support count of this lane's output position in the NEXT chunk
+    unsigned armw;
+    int cnt;
+};
+
 template <bool NONNEG, bool HAS_SUP, bool EDGE>
-__device__ __forceinline__ void seq_chunk(pair2& acc, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
+__device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
                                           const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane) {
-    // ---- loads of the next chunk (consumed one chunk later)
+    // ---- loads of chunk tb + 2*32 (consumed two chunks later: with 8 warps per SM one chunk of loads in flight per
+    // warp does not cover the DRAM latency -- ncu showed 35 % of all stall samples on the first use of a chunk)
     {
         const float* p = src_next;
 #pragma unroll
         for (int k = 0; k < SEQ_CH; ++k) {
             if (EDGE)
-                vload[k] = (tb + SEQ_CH + k < len && act) ? __ldg(p) : 0.f;
+                vload[k] = (tb + 2 * SEQ_CH + k < len && act) ? __ldg(p) : 0.f;
             else
                 vload[k] = __ldg(p);
             p += step;
         }
     }
-    // ---- descriptors of the outputs of this chunk: position tb - 35 + lane
+    // ---- descriptors of the outputs of this chunk (position tb - 35 + lane) from the arm word / count fetched one
+    // chunk ago; fetch the next chunk's now so that load is never on the critical path
     {
         const int j = tb - SEQ_LOOK + lane;
         Desc ds{0u, 0u, 1.f, 1.f};
         if (!EDGE || (j >= 0 && j < len)) {
-            const long long pix = pbase + pstride * j;
-            const uchar4 a = __ldg(arms + pix);
-            const int lo = horiz ? a.x : a.z, hi = horiz ? a.y : a.w;
+            const int lo = (int)(pre.armw & 0xffu), hi = (int)(pre.armw >> 8);
             const int sa = (j - lo) % SEQ_R, sb = (j + hi + 1) % SEQ_R;  // j - lo >= 0: arms stop at the image border
             ds.offa = (unsigned)sa * 256u;
             ds.offb = (unsigned)sb * 256u;
             if (HAS_SUP) {
-                ds.cnt = (float)(int)__ldg(sup + pix);
+                ds.cnt = (float)pre.cnt;
                 ds.rcp = __frcp_rn(ds.cnt);
             }
+        }
+        const int jn = j + SEQ_CH;
+        pre.armw = 0u;
+        pre.cnt = 1;
+        if (jn >= 0 && jn < len) {
+            const long long pix = pbase + pstride * jn;
+            const uchar4 a = __ldg(arms + pix);
+            pre.armw = horiz ? ((unsigned)a.x | ((unsigned)a.y << 8)) : ((unsigned)a.z | ((unsigned)a.w << 8));
+            if (HAS_SUP) pre.cnt = (int)__ldg(sup + pix);
         }
         __syncwarp();  // the previous chunk's descriptor reads are done
         desc[lane] = ds;
@@ -122,17 +136,22 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, float (&vuse)[SEQ_CH], flo
     }
 }
 
+constexpr int SEQ_WARPS = 8;  // the 8 warps of a block walk the d-chunks of the same line(s): 1 KB contiguous per pixel
+constexpr int SEQ_SMEM_PER_WARP = SEQ_R * 256 + SEQ_CH * (int)sizeof(Desc);
+
 template <bool NONNEG, bool HAS_SUP>
-__global__ void __launch_bounds__(32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
                                                      int D, int horiz, float bias) {
-    __shared__ __align__(16) unsigned char s_ring[SEQ_R * 256];  // [slot][lane] float2
-    __shared__ Desc s_desc[SEQ_CH];
-    const int lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
+    Desc* s_desc = reinterpret_cast<Desc*>(s_ring + SEQ_R * 256);
     const int nchunk = (D + 31) >> 5;
-    const long long wg = blockIdx.x;
+    const long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
     const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
     const int len = horiz ? W : H;
+    if (line >= (horiz ? H : W)) return;  // whole warp; warps never synchronise with each other
     const int d = chunk * 32 + lane;
     const bool act = d < D;
     const bool full = chunk * 32 + 32 <= D;  // every lane active: the interior path needs no lane predicate
@@ -144,51 +163,51 @@ __global__ void __launch_bounds__(32) agg_seq_kernel(const float* __restrict__ i
     unsigned char* ring_col = s_ring + lane * 8;
 
     pair2 acc{NONNEG ? bias : 0.f, 0.f};
-    float va[SEQ_CH], vb[SEQ_CH];  // two register buffers: a chunk's loads stay in flight for a whole chunk
+    // three register buffers rotate: while chunk o is consumed, chunks o+1 and o+2 are in flight (8 KB per warp)
+    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
 #pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) va[k] = (k < len && act) ? __ldg(src + step * k) : 0.f;
-
-    // chunk ob covers prefix positions [32*ob, 32*ob+32) and outputs [32*ob-35, 32*ob-3); outputs end at len-1
-    const int nouter = (len + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;
-    for (int ob = 0; ob < nouter; ob += 2) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int o = ob + half;
-            if (o >= nouter) break;
-            const int tb = o * SEQ_CH;
-            const float* src_next = src + step * (tb + SEQ_CH);
-            float* dst_first = dst + step * (tb - SEQ_LOOK);
-            // interior: next chunk fully inside the line, all outputs of this chunk inside the line, all lanes active
-            const bool interior = full && tb - SEQ_LOOK >= 0 && tb + 2 * SEQ_CH <= len;
-            if (half == 0) {
-                if (interior)
-                    seq_chunk<NONNEG, HAS_SUP, false>(acc, va, vb, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms,
-                                                      sup, ring_col, s_desc, lane);
-                else
-                    seq_chunk<NONNEG, HAS_SUP, true>(acc, va, vb, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms, sup,
-                                                     ring_col, s_desc, lane);
-            } else {
-                if (interior)
-                    seq_chunk<NONNEG, HAS_SUP, false>(acc, vb, va, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms,
-                                                      sup, ring_col, s_desc, lane);
-                else
-                    seq_chunk<NONNEG, HAS_SUP, true>(acc, vb, va, tb, len, act, src_next, dst_first, step, pbase, pstride, horiz, arms, sup,
-                                                     ring_col, s_desc, lane);
-            }
-        }
+    for (int k = 0; k < SEQ_CH; ++k) {
+        va[k] = (k < len && act) ? __ldg(src + step * k) : 0.f;
+        vb[k] = (SEQ_CH + k < len && act) ? __ldg(src + step * (SEQ_CH + k)) : 0.f;
     }
+
+    Prefetched pre{0u, 1};  // chunk 0 outputs positions -35..-4: nothing to fetch; its call fetches chunk 1's
+    // chunk o covers prefix positions [32*o, 32*o+32) and outputs [32*o-35, 32*o-3); outputs end at len-1
+    const int nouter = (len + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;
+#define SMT_SEQ_STEP(USE, LOAD)                                                                                               \
+    if (o < nouter) {                                                                                                         \
+        const int tb = o * SEQ_CH;                                                                                            \
+        const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                               \
+        float* dst_first = dst + step * (tb - SEQ_LOOK);                                                                      \
+        /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
+        if (full && tb - SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                             \
+            seq_chunk<NONNEG, HAS_SUP, false>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,   \
+                                              horiz, arms, sup, ring_col, s_desc, lane);                                      \
+        else                                                                                                                  \
+            seq_chunk<NONNEG, HAS_SUP, true>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,    \
+                                             horiz, arms, sup, ring_col, s_desc, lane);                                       \
+        ++o;                                                                                                                  \
+    }
+    for (int o = 0; o < nouter;) {
+        SMT_SEQ_STEP(va, vc)
+        SMT_SEQ_STEP(vb, va)
+        SMT_SEQ_STEP(vc, vb)
+    }
+#undef SMT_SEQ_STEP
 }
 
 template <bool NONNEG, bool HAS_SUP>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
                                int horiz, float bias) {
+    constexpr size_t smem = (size_t)SEQ_WARPS * SEQ_SMEM_PER_WARP;
     static bool attr_set = false;
-    if (!attr_set) {  // ~25 KB of static shared memory per one-warp block: ask for the largest carveout (9 blocks / SM)
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (!attr_set) {
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
-    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP>), (unsigned)nwarps, 32, 0, in, out, arms, sup, H, W, D, horiz, bias);
+    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
+               bias);
     return SMT_OK;
 }
 
