@@ -91,7 +91,9 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
         Desc ds{0u, 0u, 1.f, 1.f};
         if (!EDGE || (j >= 0 && j < len)) {
             const int lo = (int)(pre.armw & 0xffu), hi = (int)(pre.armw >> 8);
-            const int sa = (j - lo) % SEQ_R, sb = (j + hi + 1) % SEQ_R;  // j - lo >= 0: arms stop at the image border
+            // arms stop at the image border, so the clamps only act on the halo rows of a row band (bandsplit), whose
+            // results are never used
+            const int sa = max(j - lo, 0) % SEQ_R, sb = min(j + hi + 1, len) % SEQ_R;
             ds.offa = (unsigned)sa * 256u;
             ds.offb = (unsigned)sb * 256u;
             if (HAS_SUP) {
@@ -222,3 +224,40 @@ smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uin
     return sup ? launch_seq<false, true>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
                : launch_seq<false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
 }
+
+// ---------------------------------------------------------------------------------------------- per-sweep C ABI (row bands)
+extern "C" {
+
+int32_t smt_cross_sweep_count(int32_t iters) { return iters > 0 ? 2 * iters : 0; }
+
+// sweep s of `iters` iterations: direction and whether it divides by a support count (cross_aggregator.cpp:102-117)
+smt_status_t smt_cross_sweep_info(int32_t iters, int32_t sweep, int32_t* horizontal, int32_t* divides) {
+    if (sweep < 0 || sweep >= 2 * iters || !horizontal || !divides) return SMT_ERR_INVALID_ARG;
+    const bool hfirst = (sweep / 2) % 2 == 0;
+    const bool second = sweep % 2 == 1;
+    *horizontal = (hfirst != second) ? 1 : 0;
+    *divides = second ? 1 : 0;
+    return SMT_OK;
+}
+
+smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t sweep, const float* vol_in, float* vol_out,
+                                       const uint8_t* arms, const uint16_t* sup_hfirst, const uint16_t* sup_vfirst, int32_t rows,
+                                       int32_t cols, int32_t D, float vmax, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, space == SMT_DEVICE, SMT_ERR_UNSUPPORTED, "smt_aggregate_cross_sweep: device memspace only");
+    SMT_REQUIRE(ctx, vol_in && vol_out && vol_in != vol_out && arms && sup_hfirst && sup_vfirst && rows > 0 && cols > 0 && D > 0,
+                SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: bad argument");
+    int32_t horiz = 0, divides = 0;
+    if (smt_cross_sweep_info(iters, sweep, &horiz, &divides) != SMT_OK)
+        return smt_fail(ctx, SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: sweep %d outside 0..%d", sweep, 2 * iters - 1);
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer t(ctx, ST_AGGREGATE);
+    const bool hfirst = (sweep / 2) % 2 == 0;
+    const uint16_t* sup = divides ? (hfirst ? sup_hfirst : sup_vfirst) : nullptr;
+    const bool nonneg = vmax > 0.f && vmax < 1e30f;
+    float b = 1.f;
+    while (nonneg && b < vmax) b *= 2.f;
+    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, divides ? b * 128.f : b);
+}
+
+}  // extern "C"
