@@ -23,6 +23,7 @@ namespace {
 constexpr int SEQ_R = 96;     // ring entries: three chunks
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
 constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
+constexpr int SEQ_PF = 0;     // L2 bulk-prefetch distance in chunks beyond the register loads (0 = off)
 
 struct pair2 {
     float a, b;
@@ -61,7 +62,7 @@ struct __align__(16) Desc {
 // One chunk of 32 positions starting at tb (a multiple of 32).  Loads chunk tb+32 into `vload`, consumes `vuse`
 // (chunk tb): 32 prefix steps (E[tb+k] is stored BEFORE v[tb+k] is added, so slots never wrap inside a chunk), and
 // after every 8 of them the 8 outputs j = tb+kk-35 that have become computable.  EDGE adds the range predicates.
-struct Prefetched {  // arm word (lo | hi << 8) and support count of this lane's output position in the NEXT chunk
+struct Prefetched {  // raw uchar4 arm word and support count of this lane's output position in the NEXT chunk
     unsigned armw;
     int cnt;
 };
@@ -70,7 +71,8 @@ template <bool NONNEG, bool HAS_SUP, bool EDGE>
 __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
                                           const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
-                                          const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane) {
+                                          const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
+                                          const float* pf_base) {
     // ---- loads of chunk tb + 2*32 (consumed two chunks later: with 8 warps per SM one chunk of loads in flight per
     // warp does not cover the DRAM latency -- ncu showed 35 % of all stall samples on the first use of a chunk)
     {
@@ -78,10 +80,19 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 #pragma unroll
         for (int k = 0; k < SEQ_CH; ++k) {
             if (EDGE)
-                vload[k] = (tb + 2 * SEQ_CH + k < len && act) ? __ldg(p) : 0.f;
+                vload[k] = (tb + 2 * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
             else
-                vload[k] = __ldg(p);
+                vload[k] = __ldcs(p);
             p += step;
+        }
+        // L2 bulk prefetch (TMA unit, no registers): the warp's 128-byte rows SEQ_PF chunks beyond the register loads;
+        // lane k asks for position k of that chunk
+        if (SEQ_PF > 0) {
+            const int tp = tb + (2 + SEQ_PF) * SEQ_CH + lane;
+            if (tp < len && pf_base) {
+                const float* q = pf_base + step * tp;  // start of this warp's 32 disparities of that row (16-byte aligned)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(q) : "memory");
+            }
         }
     }
     // ---- descriptors of the outputs of this chunk (position tb - 35 + lane) from the arm word / count fetched one
@@ -90,7 +101,9 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
         const int j = tb - SEQ_LOOK + lane;
         Desc ds{0u, 0u, 1.f, 1.f};
         if (!EDGE || (j >= 0 && j < len)) {
-            const int lo = (int)(pre.armw & 0xffu), hi = (int)(pre.armw >> 8);
+            // unpack here, a whole chunk after the load was issued (unpacking next to the load stalls on it)
+            const unsigned aw = horiz ? (pre.armw & 0xffffu) : (pre.armw >> 16);
+            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
             // arms stop at the image border, so the clamps only act on the halo rows of a row band (bandsplit), whose
             // results are never used
             const int sa = max(j - lo, 0) % SEQ_R, sb = min(j + hi + 1, len) % SEQ_R;
@@ -106,8 +119,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
         pre.cnt = 1;
         if (jn >= 0 && jn < len) {
             const long long pix = pbase + pstride * jn;
-            const uchar4 a = __ldg(arms + pix);
-            pre.armw = horiz ? ((unsigned)a.x | ((unsigned)a.y << 8)) : ((unsigned)a.z | ((unsigned)a.w << 8));
+            pre.armw = __ldg(reinterpret_cast<const unsigned*>(arms) + pix);  // raw {left,right,top,bottom} bytes
             if (HAS_SUP) pre.cnt = (int)__ldg(sup + pix);
         }
         __syncwarp();  // the previous chunk's descriptor reads are done
@@ -130,7 +142,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                     const float2 eb = *reinterpret_cast<const float2*>(ring_col + ds.offb);
                     float r = __fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y));
                     if (HAS_SUP) r = div_by_count(r, ds.cnt, ds.rcp);
-                    if (!EDGE || act) *dp = r;
+                    if (!EDGE || act) __stcs(dp, r);
                 }
                 dp += step;
             }
@@ -163,14 +175,16 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
     const float* src = in + pbase * D + (act ? d : 0);
     float* dst = out + pbase * D + (act ? d : 0);
     unsigned char* ring_col = s_ring + lane * 8;
+    // bulk prefetch needs 16-byte aligned 128-byte rows fully inside the volume
+    const float* pf_base = (full && (D & 3) == 0) ? in + pbase * D + chunk * 32 : nullptr;
 
     pair2 acc{NONNEG ? bias : 0.f, 0.f};
     // three register buffers rotate: while chunk o is consumed, chunks o+1 and o+2 are in flight (8 KB per warp)
     float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
-        va[k] = (k < len && act) ? __ldg(src + step * k) : 0.f;
-        vb[k] = (SEQ_CH + k < len && act) ? __ldg(src + step * (SEQ_CH + k)) : 0.f;
+        va[k] = (k < len && act) ? __ldcs(src + step * k) : 0.f;
+        vb[k] = (SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
     }
 
     Prefetched pre{0u, 1};  // chunk 0 outputs positions -35..-4: nothing to fetch; its call fetches chunk 1's
@@ -184,10 +198,10 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
         /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
         if (full && tb - SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                             \
             seq_chunk<NONNEG, HAS_SUP, false>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,   \
-                                              horiz, arms, sup, ring_col, s_desc, lane);                                      \
+                                              horiz, arms, sup, ring_col, s_desc, lane, pf_base);                             \
         else                                                                                                                  \
             seq_chunk<NONNEG, HAS_SUP, true>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,    \
-                                             horiz, arms, sup, ring_col, s_desc, lane);                                       \
+                                             horiz, arms, sup, ring_col, s_desc, lane, pf_base);                              \
         ++o;                                                                                                                  \
     }
     for (int o = 0; o < nouter;) {
