@@ -264,6 +264,7 @@ def gpu_arm(args, H, W, D):
     alg = {"cost": 2 * V, "aggregate": 2 * V * iters * 2, "scanline": 2 * V, "wta": 1 * V}   # SURVEY.md 8(d), both views
     kern = {"cost": "adcensus_cost_kernel", "aggregate": "agg_seq_kernel" if mode == SUM_FAST else "agg_pass_exact_kernel",
             "scanline": "scan_path_kernel", "wta": "wta_first_min_kernel"}
+    nlaunch = {"cost": 2, "aggregate": 4 * iters if mode == SUM_FAST else 4 * iters, "scanline": 4, "wta": 1}  # per frame
     dom = max(alg, key=lambda k: st.get(k, 0.0))
     peak, how = measured_hbm_peak()
     ach = alg[dom] / (st[dom] / 1e3) / 1e9
@@ -276,7 +277,8 @@ def gpu_arm(args, H, W, D):
             traffic = None
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": kern[dom], "peak_source": how,
-                "algorithmic_bytes_per_frame": alg[dom], "stage_ms_per_frame": st[dom],
+                "algorithmic_bytes_per_launch": alg[dom] / nlaunch[dom], "avg_launch_ms": st[dom] / nlaunch[dom],
+                "launches_per_frame": nlaunch[dom], "algorithmic_bytes_per_frame": alg[dom], "stage_ms_per_frame": st[dom],
                 "all_stages": {k: {"ms_per_frame": st.get(k, 0.0), "algorithmic_GBps": (alg[k] / (st[k] / 1e3) / 1e9) if st.get(k) else None}
                                for k in alg},
                 "other_stage_ms_per_frame": {k: v for k, v in st.items() if k not in alg}}
