@@ -223,6 +223,8 @@ struct Pass {
 
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
                             int horiz, bool nonneg, float bias);  // cross_agg_seq.cu
+smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
+                            int horiz, bool nonneg, float bias_a, float bias_b);
 
 // vmax: an upper bound of the (non-negative) input values, or <= 0 when the sign/range of the input is unknown.
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
@@ -252,13 +254,24 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
     float b_plain = 1.f;  // power of two >= vmax: bias of a pass whose input is a cost (or an average of costs)
     while (nonneg && b_plain < vmax) b_plain *= 2.f;
     const float b_sum = b_plain * 128.f;  // input of a dividing pass: sums of <= 69 such values
-    static const bool fuse_pairs = getenv("SMT_AGG_NO_FUSE") == nullptr;
+    // fused V,V / H,H walks halve the traffic of those passes but need two rings per warp (4 warps per SM); measured
+    // 23.7 ms vs 21.0 ms per 1080p x 256 frame, so they are opt-in (SMT_AGG_FUSE=1)
+    static const bool fuse_pairs = getenv("SMT_AGG_FUSE") != nullptr;
     // default: the streaming one-warp-per-line kernel (cross_agg_seq.cu); SMT_AGG_KERNEL=tile selects the tiled one
     static const bool use_tile = getenv("SMT_AGG_KERNEL") != nullptr && std::string(getenv("SMT_AGG_KERNEL")) == "tile";
     if (!use_tile) {
-        for (size_t k = 0; k < passes.size(); ++k) {
-            SMT_TRY(k_agg_seq_pass(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg,
-                                   passes[k].sup ? b_sum : b_plain));
+        for (size_t k = 0; k < passes.size();) {
+            // a dividing pass followed by a non-dividing pass in the same direction (V,V / H,H) runs as one fused walk
+            const bool pair = fuse_pairs && k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz && passes[k].sup &&
+                              !passes[k + 1].sup;
+            if (pair) {
+                SMT_TRY(k_agg_seq_pair(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg, b_sum, b_plain));
+                k += 2;
+            } else {
+                SMT_TRY(k_agg_seq_pass(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg,
+                                       passes[k].sup ? b_sum : b_plain));
+                k += 1;
+            }
             float* sw = cur;
             cur = oth;
             oth = sw;

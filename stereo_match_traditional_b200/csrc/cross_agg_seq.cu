@@ -212,6 +212,180 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
 #undef SMT_SEQ_STEP
 }
 
+// ================================================================================================ fused pass pair
+// Two consecutive passes along the SAME direction (the reference's order H,V | V,H | H,V | V,H contains V,V and H,H
+// pairs) in one walk: pass A's outputs are consumed, in order, as pass B's input, so the intermediate volume is never
+// written or read.  A-output j appears when the A-prefix has reached j+35; B-output i when the B-prefix (over A's
+// outputs) has reached i+35, i.e. 70 positions behind the loads.  Pass A is the second pass of an iteration (divides
+// by its support count), pass B the first pass of the next one (no division).  Ring B stores E_B[j] at slot
+// (j+35) mod 96 so that, like ring A, every store inside a chunk has a compile-time offset.
+struct Prefetched2 {
+    unsigned armw_a, armw_b;
+    int cnt_a;
+};
+
+template <bool NONNEG, bool EDGE>
+__device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetched2& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH],
+                                           int tb, int len, bool act, const float* __restrict__ src_next, float* __restrict__ dst_first,
+                                           long long step, long long pbase, long long pstride, int horiz,
+                                           const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_a,
+                                           unsigned char* ring_b, Desc* desc_a, Desc* desc_b, int lane) {
+    {
+        const float* p = src_next;
+#pragma unroll
+        for (int k = 0; k < SEQ_CH; ++k) {
+            if (EDGE)
+                vload[k] = (tb + 2 * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+            else
+                vload[k] = __ldcs(p);
+            p += step;
+        }
+    }
+    {
+        const int ja = tb - SEQ_LOOK + lane, ib = ja - SEQ_LOOK;
+        Desc da{0u, 0u, 1.f, 1.f}, db{0u, 0u, 1.f, 1.f};
+        if (!EDGE || (ja >= 0 && ja < len)) {
+            const unsigned aw = horiz ? (pre.armw_a & 0xffffu) : (pre.armw_a >> 16);
+            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
+            da.offa = (unsigned)(max(ja - lo, 0) % SEQ_R) * 256u;
+            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQ_R) * 256u;
+            da.cnt = (float)pre.cnt_a;
+            da.rcp = __frcp_rn(da.cnt);
+        }
+        if (!EDGE || (ib >= 0 && ib < len)) {
+            const unsigned aw = horiz ? (pre.armw_b & 0xffffu) : (pre.armw_b >> 16);
+            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
+            db.offa = (unsigned)((max(ib - lo, 0) + SEQ_LOOK) % SEQ_R) * 256u;          // E_B[j] lives at slot (j+35) mod R
+            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQ_LOOK) % SEQ_R) * 256u;
+        }
+        const int jn = ja + SEQ_CH, in_ = ib + SEQ_CH;
+        pre.armw_a = pre.armw_b = 0u;
+        pre.cnt_a = 1;
+        if (jn >= 0 && jn < len) {
+            const long long pix = pbase + pstride * jn;
+            pre.armw_a = __ldg(arms + pix);
+            pre.cnt_a = (int)__ldg(sup_a + pix);
+        }
+        if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_);
+        __syncwarp();
+        desc_a[lane] = da;
+        desc_b[lane] = db;
+        __syncwarp();
+    }
+    const unsigned woff = (unsigned)(tb % SEQ_R) * 256u;
+    unsigned char* wa = ring_a + woff;  // slot of E_A[tb]
+    unsigned char* wb = ring_b + woff;  // slot of E_B[tb-35]
+    float* dp = dst_first;              // output position tb - 70
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) {
+        *reinterpret_cast<float2*>(wa + k * 256) = make_float2(acc_a.a, acc_a.b);  // E_A[tb+k]
+        acc_a = pre_add<NONNEG>(acc_a, vuse[k]);
+        if ((k & 7) == 7) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kk = k - 7 + u;
+                // ---- pass A output j = tb+kk-35, fed straight into pass B's prefix
+                float a = 0.f;
+                if (!EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len)) {
+                    const Desc ds = desc_a[kk];
+                    const float2 ea = *reinterpret_cast<const float2*>(ring_a + ds.offa);
+                    const float2 eb = *reinterpret_cast<const float2*>(ring_a + ds.offb);
+                    a = div_by_count(__fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y)), ds.cnt, ds.rcp);
+                }
+                *reinterpret_cast<float2*>(wb + kk * 256) = make_float2(acc_b.a, acc_b.b);  // E_B[j]
+                acc_b = pre_add<NONNEG>(acc_b, a);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kk = k - 7 + u;
+                // ---- pass B output i = tb+kk-70 (needs E_B up to i+35 = j, stored just above)
+                if (!EDGE || (tb - 2 * SEQ_LOOK + kk >= 0 && tb - 2 * SEQ_LOOK + kk < len)) {
+                    const Desc ds = desc_b[kk];
+                    const float2 ea = *reinterpret_cast<const float2*>(ring_b + ds.offa);
+                    const float2 eb = *reinterpret_cast<const float2*>(ring_b + ds.offb);
+                    const float r = __fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y));
+                    if (!EDGE || act) __stcs(dp, r);
+                }
+                dp += step;
+            }
+        }
+    }
+}
+
+constexpr int SEQ2_WARPS = 4;
+constexpr int SEQ2_SMEM_PER_WARP = 2 * SEQ_R * 256 + 2 * SEQ_CH * (int)sizeof(Desc);
+
+template <bool NONNEG>
+__global__ void __launch_bounds__(SEQ2_WARPS * 32) agg_seq2_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                  const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a,
+                                                                  int H, int W, int D, int horiz, float bias_a, float bias_b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * SEQ2_SMEM_PER_WARP;
+    unsigned char* ring_a = base + lane * 8;
+    unsigned char* ring_b = base + SEQ_R * 256 + lane * 8;
+    Desc* desc_a = reinterpret_cast<Desc*>(base + 2 * SEQ_R * 256);
+    Desc* desc_b = desc_a + SEQ_CH;
+    const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
+    const int nchunk = (D + 31) >> 5;
+    const long long wg = (long long)blockIdx.x * SEQ2_WARPS + warp;
+    const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
+    const int len = horiz ? W : H;
+    if (line >= (horiz ? H : W)) return;
+    const int d = chunk * 32 + lane;
+    const bool act = d < D;
+    const bool full = chunk * 32 + 32 <= D;
+    const long long pstride = horiz ? 1 : (long long)W;
+    const long long pbase = horiz ? (long long)line * W : (long long)line;
+    const long long step = pstride * D;
+    const float* src = in + pbase * D + (act ? d : 0);
+    float* dst = out + pbase * D + (act ? d : 0);
+
+    pair2 acc_a{NONNEG ? bias_a : 0.f, 0.f}, acc_b{NONNEG ? bias_b : 0.f, 0.f};
+    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) {
+        va[k] = (k < len && act) ? __ldcs(src + step * k) : 0.f;
+        vb[k] = (SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
+    }
+    Prefetched2 pre{0u, 0u, 1};
+    const int nouter = (len + 2 * SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;
+#define SMT_SEQ2_STEP(USE, LOAD)                                                                                             \
+    if (o < nouter) {                                                                                                        \
+        const int tb = o * SEQ_CH;                                                                                           \
+        const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                              \
+        float* dst_first = dst + step * (tb - 2 * SEQ_LOOK);                                                                 \
+        if (full && tb - 2 * SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                        \
+            seq2_chunk<NONNEG, false>(acc_a, acc_b, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride, \
+                                      horiz, arms, sup_a, ring_a, ring_b, desc_a, desc_b, lane);                             \
+        else                                                                                                                 \
+            seq2_chunk<NONNEG, true>(acc_a, acc_b, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,  \
+                                     horiz, arms, sup_a, ring_a, ring_b, desc_a, desc_b, lane);                              \
+        ++o;                                                                                                                 \
+    }
+    for (int o = 0; o < nouter;) {
+        SMT_SEQ2_STEP(va, vc)
+        SMT_SEQ2_STEP(vb, va)
+        SMT_SEQ2_STEP(vc, vb)
+    }
+#undef SMT_SEQ2_STEP
+}
+
+template <bool NONNEG>
+static smt_status_t launch_seq2(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
+                                int horiz, float bias_a, float bias_b) {
+    constexpr size_t smem = (size_t)SEQ2_WARPS * SEQ2_SMEM_PER_WARP;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq2_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    SMT_LAUNCH(ctx, (agg_seq2_kernel<NONNEG>), cdiv(nwarps, SEQ2_WARPS), SEQ2_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
+               bias_b);
+    return SMT_OK;
+}
+
 template <bool NONNEG, bool HAS_SUP>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
                                int horiz, float bias) {
@@ -237,6 +411,14 @@ smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uin
                    : launch_seq<true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
     return sup ? launch_seq<false, true>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
                : launch_seq<false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+}
+
+// pass A (divides by sup_a) followed by pass B (no division) along the same direction, in one walk
+smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
+                            int horiz, bool nonneg, float bias_a, float bias_b) {
+    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    return nonneg ? launch_seq2<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
+                  : launch_seq2<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
 }
 
 // ---------------------------------------------------------------------------------------------- per-sweep C ABI (row bands)
