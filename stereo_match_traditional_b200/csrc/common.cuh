@@ -197,7 +197,8 @@ smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1
                           uint16_t* sup0, uint16_t* sup1);
 // aggregates `vol` (modified: ping-pongs between vol and tmp); *result points at whichever buffer holds the answer
 smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
-                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result);
+                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result,
+                               float* wta_disp = nullptr);
 smt_status_t k_scanline(smt_ctx* ctx, const float* cost, const float* gray, int H, int W, int D, int p1, int p2,
                         float* left, float* right, float* up, float* down, float* sum, float* disp, float* scratch_a,
                         float* scratch_b);

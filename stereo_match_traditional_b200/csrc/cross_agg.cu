@@ -117,11 +117,12 @@ __global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------- fast line passes
 // (implemented in cross_agg_fast.cu)
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
-                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result);
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result, float* wta_disp);
 
 smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
-                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result) {
-    if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, vmax, result);
+                               const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result,
+                               float* wta_disp) {
+    if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, vmax, result, wta_disp);
     StageTimer t(ctx, ST_AGGREGATE);
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     const size_t ncell = (size_t)H * W * D;
@@ -140,6 +141,7 @@ smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8
         hfirst = !hfirst;
     }
     *result = cur;  // every iteration ends back in `vol`
+    if (wta_disp) SMT_TRY(k_wta(ctx, cur, H, W, D, wta_disp));
     return SMT_OK;
 }
 

@@ -225,10 +225,12 @@ smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uin
                             int horiz, bool nonneg, float bias);  // cross_agg_seq.cu
 smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
                             int horiz, bool nonneg, float bias_a, float bias_b);
+smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D, int horiz,
+                                float bias, float* disp);
 
 // vmax: an upper bound of the (non-negative) input values, or <= 0 when the sign/range of the input is unknown.
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
-                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result) {
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result, float* wta_disp) {
     StageTimer t(ctx, ST_AGGREGATE);
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     // pass list (cross_aggregator.cpp:102-117): horizontal-first on even iterations; the second pass divides
@@ -264,6 +266,12 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
             // a dividing pass followed by a non-dividing pass in the same direction (V,V / H,H) runs as one fused walk
             const bool pair = fuse_pairs && k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz && passes[k].sup &&
                               !passes[k + 1].sup;
+            // the last pass feeds only a winner-take-all: reduce in the kernel, never write the volume
+            if (wta_disp && nonneg && k + 1 == passes.size() && passes[k].sup) {
+                SMT_TRY(k_agg_seq_pass_wta(ctx, cur, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, b_sum, wta_disp));
+                *result = nullptr;
+                return SMT_OK;
+            }
             if (pair) {
                 SMT_TRY(k_agg_seq_pair(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg, b_sum, b_plain));
                 k += 2;
@@ -277,6 +285,7 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
             oth = sw;
         }
         *result = cur;
+        if (wta_disp) SMT_TRY(k_wta(ctx, cur, H, W, D, wta_disp));
         return SMT_OK;
     }
     for (size_t k = 0; k < passes.size();) {
@@ -313,5 +322,6 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
         oth = sw;
     }
     *result = cur;
+    if (wta_disp) SMT_TRY(k_wta(ctx, cur, H, W, D, wta_disp));
     return SMT_OK;
 }

@@ -67,12 +67,20 @@ struct Prefetched {  // raw uchar4 arm word and support count of this lane's out
     int cnt;
 };
 
-template <bool NONNEG, bool HAS_SUP, bool EDGE>
+__device__ __forceinline__ unsigned f2key_(float f) {  // order-preserving float -> uint
+    const unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f_(unsigned k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+
+// WTA: instead of storing the pass output, reduce it over the warp's 32 disparities (first minimum) and store one
+// (value, d) pair per position and d-chunk; wta_reduce_kernel finishes the arg-min over the chunks.
+template <bool NONNEG, bool HAS_SUP, bool EDGE, bool WTA>
 __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
                                           const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
-                                          const float* pf_base) {
+                                          const float* pf_base, float2* __restrict__ wta_first, long long wta_step, int d) {
     // ---- loads of chunk tb + 2*32 (consumed two chunks later: with 8 warps per SM one chunk of loads in flight per
     // warp does not cover the DRAM latency -- ncu showed 35 % of all stall samples on the first use of a chunk)
     {
@@ -128,6 +136,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
     }
     unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;  // slot of E[tb]
     float* dp = dst_first;                                             // output position tb - 35
+    float2* wp = wta_first;
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
         *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E[tb+k]
@@ -142,9 +151,17 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                     const float2 eb = *reinterpret_cast<const float2*>(ring_col + ds.offb);
                     float r = __fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y));
                     if (HAS_SUP) r = div_by_count(r, ds.cnt, ds.rcp);
-                    if (!EDGE || act) __stcs(dp, r);
+                    if (WTA) {
+                        const unsigned key = act ? f2key_(r) : 0xffffffffu;
+                        const unsigned g = __reduce_min_sync(0xffffffffu, key);
+                        const unsigned who = __ballot_sync(0xffffffffu, key == g);
+                        if (lane == 0) *wp = make_float2(key2f_(g), (float)(d + __ffs(who) - 1));  // d = this warp's first disparity
+                    } else if (!EDGE || act) {
+                        __stcs(dp, r);
+                    }
                 }
                 dp += step;
+                wp += wta_step;
             }
         }
     }
@@ -153,10 +170,10 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 constexpr int SEQ_WARPS = 8;  // the 8 warps of a block walk the d-chunks of the same line(s): 1 KB contiguous per pixel
 constexpr int SEQ_SMEM_PER_WARP = SEQ_R * 256 + SEQ_CH * (int)sizeof(Desc);
 
-template <bool NONNEG, bool HAS_SUP>
+template <bool NONNEG, bool HAS_SUP, bool WTA>
 __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
-                                                     int D, int horiz, float bias) {
+                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
@@ -195,13 +212,17 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
         const int tb = o * SEQ_CH;                                                                                            \
         const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                               \
         float* dst_first = dst + step * (tb - SEQ_LOOK);                                                                      \
+        float2* wta_first = WTA ? wta_partial + (pbase + pstride * (tb - SEQ_LOOK)) * nchunk + chunk : nullptr;               \
+        const long long wta_step = pstride * nchunk;                                                                          \
         /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
         if (full && tb - SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                             \
-            seq_chunk<NONNEG, HAS_SUP, false>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,   \
-                                              horiz, arms, sup, ring_col, s_desc, lane, pf_base);                             \
+            seq_chunk<NONNEG, HAS_SUP, false, WTA>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,       \
+                                                   pstride, horiz, arms, sup, ring_col, s_desc, lane, pf_base, wta_first,      \
+                                                   wta_step, chunk * 32);                                                     \
         else                                                                                                                  \
-            seq_chunk<NONNEG, HAS_SUP, true>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,    \
-                                             horiz, arms, sup, ring_col, s_desc, lane, pf_base);                              \
+            seq_chunk<NONNEG, HAS_SUP, true, WTA>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,        \
+                                                  pstride, horiz, arms, sup, ring_col, s_desc, lane, pf_base, wta_first,       \
+                                                  wta_step, chunk * 32);                                                      \
         ++o;                                                                                                                  \
     }
     for (int o = 0; o < nouter;) {
@@ -386,18 +407,18 @@ static smt_status_t launch_seq2(smt_ctx* ctx, const float* in, float* out, const
     return SMT_OK;
 }
 
-template <bool NONNEG, bool HAS_SUP>
+template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
-                               int horiz, float bias) {
+                               int horiz, float bias, float2* wta_partial = nullptr) {
     constexpr size_t smem = (size_t)SEQ_WARPS * SEQ_SMEM_PER_WARP;
     static bool attr_set = false;
     if (!attr_set) {
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
-    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
-               bias);
+    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
+               bias, wta_partial);
     return SMT_OK;
 }
 
@@ -407,10 +428,34 @@ smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uin
                             int horiz, bool nonneg, float bias) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     if (nonneg)
-        return sup ? launch_seq<true, true>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
-                   : launch_seq<true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
-    return sup ? launch_seq<false, true>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
-               : launch_seq<false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
+                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
+               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+}
+
+// chunk partials -> first-minimum disparity (ascending chunks, strict '<': AD-Census.h:359-372)
+__global__ void __launch_bounds__(256) wta_reduce_kernel(const float2* __restrict__ partial, size_t npix, int nchunk, float* __restrict__ disp) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float2 best = partial[p * nchunk];
+    for (int c = 1; c < nchunk; ++c) {
+        const float2 v = partial[p * nchunk + c];
+        if (v.x < best.x) best = v;
+    }
+    disp[p] = best.y;
+}
+
+// last (dividing) pass of an aggregation whose only consumer is a winner-take-all: the volume is never written
+smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D, int horiz,
+                                float bias, float* disp) {
+    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    const int nchunk = (D + 31) / 32;
+    const size_t npix = (size_t)H * W;
+    SMT_ALLOC(ctx, part, npix * nchunk * sizeof(float2));
+    SMT_TRY((launch_seq<true, true, true>(ctx, in, nullptr, arms, sup, H, W, D, horiz, bias, part.as<float2>())));
+    SMT_LAUNCH(ctx, wta_reduce_kernel, cdiv((long long)npix, 256), 256, 0, part.as<float2>(), npix, nchunk, disp);
+    return SMT_OK;
 }
 
 // pass A (divides by sup_a) followed by pass B (no division) along the same direction, in one walk
