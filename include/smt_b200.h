@@ -218,6 +218,24 @@ SMT_API smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uin
 SMT_API smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, const float* disp_right, int32_t rows,
                                         int32_t cols, uint8_t* out, smt_memspace_t space);
 
+/* ------------------------------------------------------------------------------------------------ pre / post (drivers)
+ * What the reference's main()s do with OpenCV around the matchers:
+ *   smt_bgr_to_gray          cvtColor(BGR2GRAY) on 8-bit images (fixed point 1868/9617/4899 >> 14)     main.cpp:19-20
+ *   smt_replicate_pad        copyMakeBorder(BORDER_REPLICATE); out is [rows+2*pad][cols+2*pad]          SADmain.cpp:47-48
+ *   smt_u8_to_f32            the uchar -> float image copies                                            main.cpp:46-55
+ *   smt_transform_to_show    TransformToShow (PostProcessing.h:137): (uchar)(int)disp, out-of-int-range floats -> 0
+ *   smt_normalize_minmax_u8  normalize(src, dst, 0, 255, NORM_MINMAX) followed by convertTo(CV_8U)     main.cpp:106-111
+ */
+SMT_API smt_status_t smt_bgr_to_gray(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int32_t cols, uint8_t* gray,
+                                     smt_memspace_t space);
+SMT_API smt_status_t smt_replicate_pad(smt_ctx* ctx, const uint8_t* img, int32_t rows, int32_t cols, int32_t pad,
+                                       uint8_t* out, smt_memspace_t space);
+SMT_API smt_status_t smt_u8_to_f32(smt_ctx* ctx, const uint8_t* img, size_t count, float* out, smt_memspace_t space);
+SMT_API smt_status_t smt_transform_to_show(smt_ctx* ctx, const float* disp, int32_t rows, int32_t cols, uint8_t* out,
+                                           smt_memspace_t space);
+SMT_API smt_status_t smt_normalize_minmax_u8(smt_ctx* ctx, const float* src, int32_t rows, int32_t cols, uint8_t* out,
+                                             smt_memspace_t space);
+
 /* ------------------------------------------------------------------------------------------------ full pipeline
  * P_full: the composition of the reference entry points above with the reference's own
  * default parameters (main.cpp:24-30, adcensus_types.h:69-70).

@@ -57,7 +57,32 @@ def crossarm_outputs(o, H, W, D, kind, seed):
     return out
 
 
+def prepost_outputs(o):
+    """Pre/post steps of the drivers.  cvtColor / copyMakeBorder / normalize are OpenCV (third-party, 3.1.0 pinned by the
+    .vcxproj files, not in the tree): their golden values come from the cv2 4.13 wheel in the build container."""
+    import cv2
+
+    rng = np.random.default_rng(77)
+    bgr = rng.integers(0, 256, (23, 37, 3), dtype=np.uint8)
+    gray = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    disp = rng.integers(0, 60, (23, 37)).astype(np.float32)
+    disp[rng.random((23, 37)) < 0.1] = np.inf
+    disp[rng.random((23, 37)) < 0.05] = 2147483648.0
+    disp[0, :5] = [0, 255, 256, 300.7, -3.2]
+    show = o.transform_to_show(disp)
+    smooth = (rng.random((23, 37)) * 50 + 3).astype(np.float32)
+    return {
+        "in_bgr": bgr, "gray": gray, "pad4": cv2.copyMakeBorder(gray, 4, 4, 4, 4, cv2.BORDER_REPLICATE),
+        "in_disp": disp, "show": show,
+        "norm_show": cv2.normalize(show, None, 0, 255, cv2.NORM_MINMAX),
+        "in_smooth": smooth,
+        "norm_smooth": cv2.normalize(smooth, None, 0, 255, cv2.NORM_MINMAX).round().clip(0, 255).astype(np.uint8),
+        "norm_smooth_cvt": cv2.convertScaleAbs(cv2.normalize(smooth, None, 0, 255, cv2.NORM_MINMAX)),
+    }
+
+
 def generate(o, golden_dir, digests, digest):
+    np.savez_compressed(golden_dir / "prepost.npz", **prepost_outputs(o))
     for name, H, W, D, kind, seed in MATCHER_CASES:
         out = matcher_outputs(o, H, W, D, kind, seed)
         digests[name] = {"shape": [H, W, D], "kind": kind, "seed": seed, "outputs": {k: digest(v) for k, v in out.items()}}

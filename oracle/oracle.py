@@ -198,6 +198,14 @@ class Oracle:
         self._fn("median")(_p(d, _f32p), _p(out, _f32p), W, H, int(k))
         return out
 
+    def transform_to_show(self, disp):
+        """TransformToShow (PostProcessing.h:137)."""
+        d = _c(disp, np.float32)
+        H, W = d.shape
+        out = np.zeros((H, W), np.uint8)
+        self._fn("transform_to_show")(_p(d, _f32p), H, W, _p(out, _u8p))
+        return out
+
     # ------------------------------------------------------------------ CrossAggregator
     def cross_aggregate(self, bgrL, bgrR, cost, L1=34, L2=17, t1=20, t2=6, iters=4):
         bgrL = _c(bgrL, np.uint8)

@@ -816,3 +816,14 @@ void orc_asw_crosscheck(const float* dispL, const float* dispR, int H, int W, ui
             out[(size_t)i * W + j] = diff > 5 ? 0 : (uint8_t)lv;
         }
 }
+
+/* TransformToShow (PostProcessing.h:137-154): `const int v = disp[..]` then (uchar)v; 0 stays 0.  A float outside the
+ * int range (+inf, 2147483648.f) is converted with cvttss2si on x86-64, which yields INT_MIN, whose low byte is 0. */
+void orc_transform_to_show(const float* disp, int H, int W, uint8_t* out) {
+    for (size_t p = 0; p < (size_t)H * W; ++p) {
+        const float f = disp[p];
+        int v = 0;
+        if (f > -2147483648.f && f < 2147483648.f) v = (int)f;
+        out[p] = (uint8_t)v;
+    }
+}

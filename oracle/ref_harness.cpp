@@ -184,6 +184,11 @@ void ref_remove_speckles(float* disp, int W, int H, int diff, unsigned min_area,
     rns_adc::RemoveSpeckles(disp, W, H, diff, min_area, invalid_val);
 }
 void ref_median(const float* in, float* out, int W, int H, int k) { rns_adc::MedianFilter(in, out, W, H, k); }
+// TransformToShow (PostProcessing.h:137): float disparity -> 8-bit display image
+void ref_transform_to_show(const float* disp, int H, int W, uint8_t* out) {
+    cv::Mat t(H, W, cv::CV_8UC1, out);
+    rns_adc::TransformToShow(const_cast<float*>(disp), t, H, W);
+}
 
 // ---------------------------------------------------------------- CrossAggregator (cross_aggregator.cpp)
 // arms: 4 bytes per pixel (left,right,top,bottom); sup0/sup1: uint16 per pixel.

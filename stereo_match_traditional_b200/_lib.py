@@ -85,6 +85,11 @@ SIGNATURES = {
     "smt_ncc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
     "smt_asw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _i, _i, _vp, _i]),
     "smt_asw_crosscheck": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
+    "smt_bgr_to_gray": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "smt_replicate_pad": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "smt_u8_to_f32": (_i, [_vp, _vp, C.c_size_t, _vp, _i]),
+    "smt_transform_to_show": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "smt_normalize_minmax_u8": (_i, [_vp, _vp, _i, _i, _vp, _i]),
     "smt_adcensus_default_params": (None, [C.POINTER(AdCensusParams), _i, _i, _i]),
     "smt_pipeline_adcensus_full": (_i, [_vp, C.POINTER(AdCensusParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
 }

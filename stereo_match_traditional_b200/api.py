@@ -353,6 +353,46 @@ class Engine:
         self._ck(self.lib.smt_asw_crosscheck(self.h, pl, pr, H, W, po, a.space))
         return out
 
+    # ------------------------------------------------------------------ pre / post (what the drivers do with OpenCV)
+    def bgr_to_gray(self, bgr):
+        a = _Args(self, bgr)
+        H, W = bgr.shape[:2]
+        pb = a.inp(bgr, np.uint8, (H, W, 3))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_bgr_to_gray(self.h, pb, H, W, po, a.space))
+        return out
+
+    def replicate_pad(self, img, pad):
+        a = _Args(self, img)
+        H, W = img.shape
+        pi = a.inp(img, np.uint8, (H, W))
+        out, po = a.out((H + 2 * pad, W + 2 * pad), np.uint8)
+        self._ck(self.lib.smt_replicate_pad(self.h, pi, H, W, int(pad), po, a.space))
+        return out
+
+    def u8_to_f32(self, img):
+        a = _Args(self, img)
+        pi = a.inp(img, np.uint8)
+        out, po = a.out(tuple(img.shape), np.float32)
+        self._ck(self.lib.smt_u8_to_f32(self.h, pi, int(np.prod(img.shape)), po, a.space))
+        return out
+
+    def transform_to_show(self, disp):
+        a = _Args(self, disp)
+        H, W = disp.shape
+        pi = a.inp(disp, np.float32, (H, W))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_transform_to_show(self.h, pi, H, W, po, a.space))
+        return out
+
+    def normalize_minmax_u8(self, src):
+        a = _Args(self, src)
+        H, W = src.shape
+        pi = a.inp(src, np.float32, (H, W))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_normalize_minmax_u8(self.h, pi, H, W, po, a.space))
+        return out
+
     # ------------------------------------------------------------------ full pipeline
     def default_params(self, H, W, D) -> AdCensusParams:
         p = AdCensusParams()

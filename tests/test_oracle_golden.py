@@ -78,3 +78,8 @@ def test_sad_optimal_disparity_quirks(oracle_port):
     assert oracle_port.sad_optimal_disparity(np.array([3, 9, 3, 7], np.float32)) == 0      # sad[0] <= min
     assert oracle_port.sad_optimal_disparity(np.array([5, 9, 7, 3], np.float32)) == 0      # best == D-1
     assert oracle_port.sad_optimal_disparity(np.array([9, 4, 4, 7], np.float32)) == 1      # first minimum
+
+
+def test_port_transform_to_show_matches_reference_golden(oracle_port):
+    z = np.load(GOLDEN / "prepost.npz")
+    assert np.array_equal(oracle_port.transform_to_show(z["in_disp"]), z["show"])
