@@ -64,7 +64,12 @@ def prepost_outputs(o):
 
     rng = np.random.default_rng(77)
     bgr = rng.integers(0, 256, (23, 37, 3), dtype=np.uint8)
-    gray = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    # OpenCV 3.1.0 (the reference's version): RGB2Gray<uchar> with yuv_shift = 14, B2Y/G2Y/R2Y = 1868/9617/4899 and
+    # CV_DESCALE rounding.  cv2 >= 4 switched to a 15-bit variant (3735/19235/9798) that differs by one grey level on
+    # ~0.4 % of random pixels, so the 3.1.0 formula is restated here instead of calling the 4.13 wheel.
+    b, g, r = (bgr[..., k].astype(np.int64) for k in range(3))
+    gray = ((1868 * b + 9617 * g + 4899 * r + 8192) >> 14).astype(np.uint8)
+    assert (gray == cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)).mean() > 0.99
     disp = rng.integers(0, 60, (23, 37)).astype(np.float32)
     disp[rng.random((23, 37)) < 0.1] = np.inf
     disp[rng.random((23, 37)) < 0.05] = 2147483648.0
