@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 
+// MODE 0: every line walks x = 0..W-1; 1: odd lines walk backwards; 2: line l starts at x = (l * 37) % W and wraps
+// (2 only probes the memory system: a prefix cannot start mid-line)
+__device__ int g_mode = 0;
 template <int VW, int BATCH>  // VW floats per lane per position (1,2,4), BATCH positions in flight per warp
 __global__ void __launch_bounds__(256) walk_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int D,
                                                    int smem_pad) {
@@ -16,18 +19,24 @@ __global__ void __launch_bounds__(256) walk_kernel(const float* __restrict__ in,
     const float* src = in + (long long)line * W * D + chunk * dchunk + lane * VW;
     float* dst = out + (long long)line * W * D + chunk * dchunk + lane * VW;
     if (smem_pad < 0) pad[threadIdx.x] = 0;  // keep the allocation alive
+    const int mode = g_mode;
     for (int x0 = 0; x0 < W; x0 += BATCH) {
         float v[BATCH][VW];
+        int xs[BATCH];
 #pragma unroll
         for (int k = 0; k < BATCH; ++k) {
-            const float* p = src + (long long)(x0 + k) * D;
+            int x = x0 + k;
+            if (mode == 1 && (line & 1)) x = W - 1 - x;
+            if (mode == 2) x = (x + line * 37) % W;
+            xs[k] = x;
+            const float* p = src + (long long)x * D;
             if (VW == 4) { float4 t = __ldcs((const float4*)p); v[k][0] = t.x; v[k][1 % VW] = t.y; v[k][2 % VW] = t.z; v[k][3 % VW] = t.w; }
             else if (VW == 2) { float2 t = __ldcs((const float2*)p); v[k][0] = t.x; v[k][1 % VW] = t.y; }
             else v[k][0] = __ldcs(p);
         }
 #pragma unroll
         for (int k = 0; k < BATCH; ++k) {
-            float* q = dst + (long long)(x0 + k) * D;
+            float* q = dst + (long long)xs[k] * D;
             if (VW == 4) __stcs((float4*)q, make_float4(v[k][0] + 1.f, v[k][1 % VW], v[k][2 % VW], v[k][3 % VW]));
             else if (VW == 2) __stcs((float2*)q, make_float2(v[k][0] + 1.f, v[k][1 % VW]));
             else __stcs(q, v[k][0] + 1.f);
@@ -62,6 +71,13 @@ int main() {
     cudaMalloc(&in, n * 4); cudaMalloc(&out, n * 4);
     cudaMemset(in, 0, n * 4);
     // occupancy limited to 1 CTA (8 warps) per SM by a 200 KB shared allocation, like agg_seq_kernel
+    for (int m = 0; m < 3; ++m) {
+        cudaMemcpyToSymbol(g_mode, &m, sizeof(int));
+        printf("-- mode %d\n", m);
+        run<1, 32>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 128B requests");
+        run<4, 8>(in, out, H, W, D, 24 * 1024, "64 warps/SM, 512B requests");
+    }
+    { int m = 0; cudaMemcpyToSymbol(g_mode, &m, sizeof(int)); }
     run<1, 32>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 128B requests");
     run<1, 64>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 128B requests");
     run<2, 32>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 256B requests");

@@ -20,9 +20,10 @@
 
 namespace {
 
-constexpr int SEQ_R = 96;     // ring entries: three chunks
+constexpr int SEQ_R = 96;     // ring entries: three 32-position chunks (span needed: 70 + SEQ_G)
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
 constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
+constexpr int SEQ_G = 8;      // outputs are emitted in groups of SEQ_G (ring span needed: 70 + SEQ_G <= SEQ_R)
 constexpr int SEQ_PF = 0;     // L2 bulk-prefetch distance in chunks beyond the register loads (0 = off)
 
 struct pair2 {
@@ -108,7 +109,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
     {
         const int j = tb - SEQ_LOOK + lane;
         Desc ds{0u, 0u, 1.f, 1.f};
-        if (!EDGE || (j >= 0 && j < len)) {
+        if ((SEQ_CH == 32 || lane < SEQ_CH) && (!EDGE || (j >= 0 && j < len))) {
             // unpack here, a whole chunk after the load was issued (unpacking next to the load stalls on it)
             const unsigned aw = horiz ? (pre.armw & 0xffffu) : (pre.armw >> 16);
             const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
@@ -125,13 +126,13 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
         const int jn = j + SEQ_CH;
         pre.armw = 0u;
         pre.cnt = 1;
-        if (jn >= 0 && jn < len) {
+        if ((SEQ_CH == 32 || lane < SEQ_CH) && jn >= 0 && jn < len) {
             const long long pix = pbase + pstride * jn;
             pre.armw = __ldg(reinterpret_cast<const unsigned*>(arms) + pix);  // raw {left,right,top,bottom} bytes
             if (HAS_SUP) pre.cnt = (int)__ldg(sup + pix);
         }
         __syncwarp();  // the previous chunk's descriptor reads are done
-        desc[lane] = ds;
+        if (SEQ_CH == 32 || lane < SEQ_CH) desc[lane] = ds;
         __syncwarp();
     }
     unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;  // slot of E[tb]
@@ -141,10 +142,10 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
     for (int k = 0; k < SEQ_CH; ++k) {
         *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E[tb+k]
         acc = pre_add<NONNEG>(acc, vuse[k]);
-        if ((k & 7) == 7) {
+        if ((k & (SEQ_G - 1)) == SEQ_G - 1) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int kk = k - 7 + u;
+            for (int u = 0; u < SEQ_G; ++u) {
+                const int kk = k - (SEQ_G - 1) + u;
                 const Desc ds = desc[kk];  // broadcast
                 if (!EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len)) {
                     const float2 ea = *reinterpret_cast<const float2*>(ring_col + ds.offa);
