@@ -7,6 +7,7 @@
 // MODE 0: every line walks x = 0..W-1; 1: odd lines walk backwards; 2: line l starts at x = (l * 37) % W and wraps
 // (2 only probes the memory system: a prefix cannot start mid-line)
 __device__ int g_mode = 0;
+__device__ long long g_pitch = 0;  // row pitch in floats (0 = dense W*D)
 template <int VW, int BATCH>  // VW floats per lane per position (1,2,4), BATCH positions in flight per warp
 __global__ void __launch_bounds__(256) walk_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int D,
                                                    int smem_pad) {
@@ -16,8 +17,9 @@ __global__ void __launch_bounds__(256) walk_kernel(const float* __restrict__ in,
     const long long wg = (long long)blockIdx.x * 8 + warp;
     const int line = (int)(wg / nchunk), chunk = (int)(wg % nchunk);
     if (line >= H) return;
-    const float* src = in + (long long)line * W * D + chunk * dchunk + lane * VW;
-    float* dst = out + (long long)line * W * D + chunk * dchunk + lane * VW;
+    const long long pitch = g_pitch ? g_pitch : (long long)W * D;
+    const float* src = in + (long long)line * pitch + chunk * dchunk + lane * VW;
+    float* dst = out + (long long)line * pitch + chunk * dchunk + lane * VW;
     if (smem_pad < 0) pad[threadIdx.x] = 0;  // keep the allocation alive
     const int mode = g_mode;
     for (int x0 = 0; x0 < W; x0 += BATCH) {
@@ -68,7 +70,7 @@ int main() {
     const int H = 1080, W = 1920, D = 256;
     const size_t n = (size_t)H * W * D;
     float *in, *out;
-    cudaMalloc(&in, n * 4); cudaMalloc(&out, n * 4);
+    cudaMalloc(&in, n * 4 + (size_t)H * 16416 * 4); cudaMalloc(&out, n * 4 + (size_t)H * 16416 * 4);
     cudaMemset(in, 0, n * 4);
     // occupancy limited to 1 CTA (8 warps) per SM by a 200 KB shared allocation, like agg_seq_kernel
     for (int m = 0; m < 3; ++m) {
@@ -78,6 +80,13 @@ int main() {
         run<4, 8>(in, out, H, W, D, 24 * 1024, "64 warps/SM, 512B requests");
     }
     { int m = 0; cudaMemcpyToSymbol(g_mode, &m, sizeof(int)); }
+    for (long long extra : {0ll, 32ll, 256ll, 1184ll, 4128ll, 16416ll}) {
+        long long pitch = (long long)W * D + extra;
+        cudaMemcpyToSymbol(g_pitch, &pitch, sizeof(long long));
+        printf("-- row pitch = W*D + %lld floats\n", extra);
+        run<1, 32>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 128B requests");
+    }
+    { long long z = 0; cudaMemcpyToSymbol(g_pitch, &z, sizeof(long long)); }
     run<1, 32>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 128B requests");
     run<1, 64>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 128B requests");
     run<2, 32>(in, out, H, W, D, 200 * 1024, "8 warps/SM, 256B requests");

@@ -11,7 +11,8 @@
 //     offset; the interior chunks of a line run a predicate-free path;
 //   * per cell: 4 FADD (prefix) + 3 FADD (difference) + 3 FMA-class ops for the exact division + 1 STS.64 + 3 LDS + 1 LDG +
 //     1 STG + ~6 integer ops, against ~65 instructions for the tiled kernel in cross_agg_fast.cu;
-//   * input rows are prefetched a full chunk (4 KB per warp) ahead into a second register buffer.
+//   * input rows are prefetched two chunks (8 KB per warp) ahead in rotating register buffers.  (L2 prefetch
+//     instructions -- prefetch.global.L2 and cp.async.bulk.prefetch.L2 -- were measured: no gain / slower.)
 // Numerics are those of cross_agg_fast.cu: cascaded compensated prefix (s, c) for non-negative input (a power-of-two
 // bias keeps the FastTwoSum error term exact), general TwoSum pair otherwise; window sums are exact to ~2^-46 and
 // rounded once.  The division by the support count is the correctly rounded quotient (Markstein's residual step on the
@@ -24,7 +25,6 @@ constexpr int SEQ_R = 96;     // ring entries: three 32-position chunks (span ne
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
 constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
 constexpr int SEQ_G = 8;      // outputs are emitted in groups of SEQ_G (ring span needed: 70 + SEQ_G <= SEQ_R)
-constexpr int SEQ_PF = 0;     // L2 bulk-prefetch distance in chunks beyond the register loads (0 = off)
 
 struct pair2 {
     float a, b;
@@ -81,7 +81,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                                           const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
-                                          const float* pf_base, float2* __restrict__ wta_first, long long wta_step, int d) {
+                                          float2* __restrict__ wta_first, long long wta_step, int d) {
     // ---- loads of chunk tb + 2*32 (consumed two chunks later: with 8 warps per SM one chunk of loads in flight per
     // warp does not cover the DRAM latency -- ncu showed 35 % of all stall samples on the first use of a chunk)
     {
@@ -93,15 +93,6 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
             else
                 vload[k] = __ldcs(p);
             p += step;
-        }
-        // L2 bulk prefetch (TMA unit, no registers): the warp's 128-byte rows SEQ_PF chunks beyond the register loads;
-        // lane k asks for position k of that chunk
-        if (SEQ_PF > 0) {
-            const int tp = tb + (2 + SEQ_PF) * SEQ_CH + lane;
-            if (tp < len && pf_base) {
-                const float* q = pf_base + step * tp;  // start of this warp's 32 disparities of that row (16-byte aligned)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(q) : "memory");
-            }
         }
     }
     // ---- descriptors of the outputs of this chunk (position tb - 35 + lane) from the arm word / count fetched one
@@ -193,8 +184,6 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
     const float* src = in + pbase * D + (act ? d : 0);
     float* dst = out + pbase * D + (act ? d : 0);
     unsigned char* ring_col = s_ring + lane * 8;
-    // bulk prefetch needs 16-byte aligned 128-byte rows fully inside the volume
-    const float* pf_base = (full && (D & 3) == 0) ? in + pbase * D + chunk * 32 : nullptr;
 
     pair2 acc{NONNEG ? bias : 0.f, 0.f};
     // three register buffers rotate: while chunk o is consumed, chunks o+1 and o+2 are in flight (8 KB per warp)
@@ -218,11 +207,11 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
         /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
         if (full && tb - SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                             \
             seq_chunk<NONNEG, HAS_SUP, false, WTA>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,       \
-                                                   pstride, horiz, arms, sup, ring_col, s_desc, lane, pf_base, wta_first,      \
+                                                   pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,               \
                                                    wta_step, chunk * 32);                                                     \
         else                                                                                                                  \
             seq_chunk<NONNEG, HAS_SUP, true, WTA>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,        \
-                                                  pstride, horiz, arms, sup, ring_col, s_desc, lane, pf_base, wta_first,       \
+                                                  pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,                \
                                                   wta_step, chunk * 32);                                                      \
         ++o;                                                                                                                  \
     }
