@@ -23,7 +23,9 @@ namespace {
 
 constexpr int SEQ_R = 96;     // ring entries: three 32-position chunks (span needed: 70 + SEQ_G)
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
-constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
+constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane).  16 with SEQ_R = 80 and 5-warp blocks (10 warps/SM,
+                              // ~100 registers) was measured 3 % slower, and overlapping the other view's scanline on a
+                              // second stream gained nothing: the passes are limited by the memory system, not by occupancy
 constexpr int SEQ_G = 8;      // outputs are emitted in groups of SEQ_G (ring span needed: 70 + SEQ_G <= SEQ_R)
 
 struct pair2 {
@@ -230,13 +232,14 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
 // outputs) has reached i+35, i.e. 70 positions behind the loads.  Pass A is the second pass of an iteration (divides
 // by its support count), pass B the first pass of the next one (no division).  Ring B stores E_B[j] at slot
 // (j+35) mod 96 so that, like ring A, every store inside a chunk has a compile-time offset.
+constexpr int SEQ2_CH = 32, SEQ2_R = 96;  // the fused walk keeps the 32-position chunks and 96-entry rings
 struct Prefetched2 {
     unsigned armw_a, armw_b;
     int cnt_a;
 };
 
 template <bool NONNEG, bool EDGE>
-__device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetched2& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH],
+__device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetched2& pre, float (&vuse)[SEQ2_CH], float (&vload)[SEQ2_CH],
                                            int tb, int len, bool act, const float* __restrict__ src_next, float* __restrict__ dst_first,
                                            long long step, long long pbase, long long pstride, int horiz,
                                            const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_a,
@@ -244,9 +247,9 @@ __device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetche
     {
         const float* p = src_next;
 #pragma unroll
-        for (int k = 0; k < SEQ_CH; ++k) {
+        for (int k = 0; k < SEQ2_CH; ++k) {
             if (EDGE)
-                vload[k] = (tb + 2 * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+                vload[k] = (tb + 2 * SEQ2_CH + k < len && act) ? __ldcs(p) : 0.f;
             else
                 vload[k] = __ldcs(p);
             p += step;
@@ -258,18 +261,18 @@ __device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetche
         if (!EDGE || (ja >= 0 && ja < len)) {
             const unsigned aw = horiz ? (pre.armw_a & 0xffffu) : (pre.armw_a >> 16);
             const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            da.offa = (unsigned)(max(ja - lo, 0) % SEQ_R) * 256u;
-            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQ_R) * 256u;
+            da.offa = (unsigned)(max(ja - lo, 0) % SEQ2_R) * 256u;
+            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQ2_R) * 256u;
             da.cnt = (float)pre.cnt_a;
             da.rcp = __frcp_rn(da.cnt);
         }
         if (!EDGE || (ib >= 0 && ib < len)) {
             const unsigned aw = horiz ? (pre.armw_b & 0xffffu) : (pre.armw_b >> 16);
             const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            db.offa = (unsigned)((max(ib - lo, 0) + SEQ_LOOK) % SEQ_R) * 256u;          // E_B[j] lives at slot (j+35) mod R
-            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQ_LOOK) % SEQ_R) * 256u;
+            db.offa = (unsigned)((max(ib - lo, 0) + SEQ_LOOK) % SEQ2_R) * 256u;          // E_B[j] lives at slot (j+35) mod R
+            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQ_LOOK) % SEQ2_R) * 256u;
         }
-        const int jn = ja + SEQ_CH, in_ = ib + SEQ_CH;
+        const int jn = ja + SEQ2_CH, in_ = ib + SEQ2_CH;
         pre.armw_a = pre.armw_b = 0u;
         pre.cnt_a = 1;
         if (jn >= 0 && jn < len) {
@@ -283,12 +286,12 @@ __device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetche
         desc_b[lane] = db;
         __syncwarp();
     }
-    const unsigned woff = (unsigned)(tb % SEQ_R) * 256u;
+    const unsigned woff = (unsigned)(tb % SEQ2_R) * 256u;
     unsigned char* wa = ring_a + woff;  // slot of E_A[tb]
     unsigned char* wb = ring_b + woff;  // slot of E_B[tb-35]
     float* dp = dst_first;              // output position tb - 70
 #pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) {
+    for (int k = 0; k < SEQ2_CH; ++k) {
         *reinterpret_cast<float2*>(wa + k * 256) = make_float2(acc_a.a, acc_a.b);  // E_A[tb+k]
         acc_a = pre_add<NONNEG>(acc_a, vuse[k]);
         if ((k & 7) == 7) {
@@ -324,7 +327,7 @@ __device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetche
 }
 
 constexpr int SEQ2_WARPS = 4;
-constexpr int SEQ2_SMEM_PER_WARP = 2 * SEQ_R * 256 + 2 * SEQ_CH * (int)sizeof(Desc);
+constexpr int SEQ2_SMEM_PER_WARP = 2 * SEQ2_R * 256 + 2 * SEQ2_CH * (int)sizeof(Desc);
 
 template <bool NONNEG>
 __global__ void __launch_bounds__(SEQ2_WARPS * 32) agg_seq2_kernel(const float* __restrict__ in, float* __restrict__ out,
@@ -334,9 +337,9 @@ __global__ void __launch_bounds__(SEQ2_WARPS * 32) agg_seq2_kernel(const float* 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * SEQ2_SMEM_PER_WARP;
     unsigned char* ring_a = base + lane * 8;
-    unsigned char* ring_b = base + SEQ_R * 256 + lane * 8;
-    Desc* desc_a = reinterpret_cast<Desc*>(base + 2 * SEQ_R * 256);
-    Desc* desc_b = desc_a + SEQ_CH;
+    unsigned char* ring_b = base + SEQ2_R * 256 + lane * 8;
+    Desc* desc_a = reinterpret_cast<Desc*>(base + 2 * SEQ2_R * 256);
+    Desc* desc_b = desc_a + SEQ2_CH;
     const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
     const int nchunk = (D + 31) >> 5;
     const long long wg = (long long)blockIdx.x * SEQ2_WARPS + warp;
@@ -353,20 +356,20 @@ __global__ void __launch_bounds__(SEQ2_WARPS * 32) agg_seq2_kernel(const float* 
     float* dst = out + pbase * D + (act ? d : 0);
 
     pair2 acc_a{NONNEG ? bias_a : 0.f, 0.f}, acc_b{NONNEG ? bias_b : 0.f, 0.f};
-    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
+    float va[SEQ2_CH], vb[SEQ2_CH], vc[SEQ2_CH];
 #pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) {
+    for (int k = 0; k < SEQ2_CH; ++k) {
         va[k] = (k < len && act) ? __ldcs(src + step * k) : 0.f;
-        vb[k] = (SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
+        vb[k] = (SEQ2_CH + k < len && act) ? __ldcs(src + step * (SEQ2_CH + k)) : 0.f;
     }
     Prefetched2 pre{0u, 0u, 1};
-    const int nouter = (len + 2 * SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;
+    const int nouter = (len + 2 * SEQ_LOOK + SEQ2_CH - 1) / SEQ2_CH;
 #define SMT_SEQ2_STEP(USE, LOAD)                                                                                             \
     if (o < nouter) {                                                                                                        \
-        const int tb = o * SEQ_CH;                                                                                           \
-        const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                              \
+        const int tb = o * SEQ2_CH;                                                                                           \
+        const float* src_next = src + step * (tb + 2 * SEQ2_CH);                                                              \
         float* dst_first = dst + step * (tb - 2 * SEQ_LOOK);                                                                 \
-        if (full && tb - 2 * SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                        \
+        if (full && tb - 2 * SEQ_LOOK >= 0 && tb + 3 * SEQ2_CH <= len)                                                        \
             seq2_chunk<NONNEG, false>(acc_a, acc_b, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride, \
                                       horiz, arms, sup_a, ring_a, ring_b, desc_a, desc_b, lane);                             \
         else                                                                                                                 \
