@@ -62,6 +62,9 @@ SMT_API int32_t smt_abi_version(void);
 SMT_API smt_status_t smt_create(int32_t device, void* stream, smt_ctx** out);
 SMT_API void smt_destroy(smt_ctx* ctx);
 SMT_API smt_status_t smt_sync(smt_ctx* ctx);
+/* The context's cudaStream_t (the one given to smt_create, or its own non-blocking stream): callers that produce or
+ * consume SMT_DEVICE buffers on another stream order the two with events on this handle. */
+SMT_API void* smt_get_stream(const smt_ctx* ctx);
 SMT_API const char* smt_last_error_string(const smt_ctx* ctx);
 SMT_API const char* smt_status_string(smt_status_t st);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
@@ -188,6 +191,17 @@ SMT_API smt_status_t smt_lrcheck_and(smt_ctx* ctx, const float* disp_left, const
  * call passes +inf, which g++ folds to 2147483647 (main.cpp:93) -- pass that to reproduce it. */
 SMT_API smt_status_t smt_remove_speckles(smt_ctx* ctx, float* disp, int32_t cols, int32_t rows, int32_t diff,
                                          uint32_t min_area, int32_t invalid_val, smt_memspace_t space);
+/* Replaces FillTheHole (PostProcessing.h:156) AS WRITTEN: the function swaps the axes (width = row, height = col), so a
+ * list entry (y, x) addresses disp[y*row + x] with y < col, x < row; "invalid" is the value 65535, not +inf.  occ:
+ * n_occ (y, x) pairs; mis: in/out, capacity row*col pairs, *n_mis in/out (host pointer in both spaces): the third phase
+ * replaces the list by all 65535-valued pixels like the reference's vector assignment (:188).  Entries outside that
+ * frame return SMT_ERR_INVALID_ARG (the reference would write out of bounds).
+ * variant SMT_FILL_FIXED is the evident intent (no reference implementation exists for it): width = col, height = row,
+ * entries are the (row, col) pairs smt_lrcheck emits, invalid = +inf as smt_lrcheck writes; otherwise identical. */
+typedef enum { SMT_FILL_AS_WRITTEN = 0, SMT_FILL_FIXED = 1 } smt_fill_variant_t;
+SMT_API smt_status_t smt_fill_the_hole(smt_ctx* ctx, float* disp, int32_t row, int32_t col, int32_t disp_range,
+                                       const int32_t* occ, int32_t n_occ, int32_t* mis, int32_t* n_mis,
+                                       int32_t variant, smt_memspace_t space);
 /* Replaces MedianFilter (PostProcessing.h:314): in-bounds taps only, element sorted[n/2]; odd wnd_size <= 9. */
 SMT_API smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32_t cols, int32_t rows,
                                 int32_t wnd_size, smt_memspace_t space);

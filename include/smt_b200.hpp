@@ -268,6 +268,17 @@ inline void RemoveSpeckles(float* disparity_map, const int& width, const int& he
     const int iv = std::isinf(invalid_val) ? 2147483647 : (int)invalid_val;
     c.check(smt_remove_speckles(c.get(), disparity_map, width, height, diff_insame, min_speckle_aera, iv, SMT_HOST));
 }
+/// As written in the reference (axes swapped, invalid = 0xffff) unless variant = SMT_FILL_FIXED; `mismatch` is replaced by
+/// the third phase (:188).
+inline void FillTheHole(const int row, const int col, const int dispRange, float* dispLeft, std::vector<std::pair<int, int>>& occlusion,
+                        std::vector<std::pair<int, int>>& mismatch, Context& c = Context::Default(), int variant = SMT_FILL_AS_WRITTEN) {
+    std::vector<int32_t> o(occlusion.size() * 2), m((size_t)row * col * 2);
+    for (size_t k = 0; k < occlusion.size(); ++k) { o[2 * k] = occlusion[k].first; o[2 * k + 1] = occlusion[k].second; }
+    for (size_t k = 0; k < mismatch.size() && k < (size_t)row * col; ++k) { m[2 * k] = mismatch[k].first; m[2 * k + 1] = mismatch[k].second; }
+    int32_t nm = (int32_t)mismatch.size();
+    c.check(smt_fill_the_hole(c.get(), dispLeft, row, col, dispRange, o.data(), (int32_t)occlusion.size(), m.data(), &nm, variant, SMT_HOST));
+    detail::pairs(m, nm, mismatch, true);
+}
 inline void MedianFilter(const float* in, float* out, const int& width, const int& height, const int wnd_size, Context& c = Context::Default()) {
     c.check(smt_median(c.get(), in, out, width, height, wnd_size, SMT_HOST));
 }

@@ -86,7 +86,36 @@ def prepost_outputs(o):
     }
 
 
+FILL_CASES = [(30, 30, 16, 5), (24, 40, 12, 6), (40, 24, 20, 7), (33, 57, 8, 8)]
+
+
+def fill_inputs(H, W, D, seed, frac_ffff=0.03, npx=120):
+    """Inputs of FillTheHole in its own (axis-swapped) frame: y < W, x < H; few 0xffff pixels so that the reference's
+    third phase stays inside its fill vector (PostProcessing.h:177 vs :188)."""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, D, (H, W)).astype(np.float32)
+    d[rng.random((H, W)) < frac_ffff] = 65535.0
+    d[rng.random((H, W)) < 0.05] = np.inf
+    lists = []
+    for _ in range(2):
+        l = np.stack([rng.integers(0, W, npx), rng.integers(0, H, npx)], 1).astype(np.int32)
+        lists.append(l[np.lexsort((l[:, 1], l[:, 0]))])
+    return d, lists[0], lists[1]
+
+
+def fill_outputs(o):
+    out = {}
+    for H, W, D, seed in FILL_CASES:
+        d, occ, mis = fill_inputs(H, W, D, seed)
+        assert (d == 65535).sum() <= len(mis)
+        f, m = o.fill_the_hole(d, D, occ, mis)
+        out[f"fill_{H}x{W}x{D}"] = f
+        out[f"mis_{H}x{W}x{D}"] = m
+    return out
+
+
 def generate(o, golden_dir, digests, digest):
+    np.savez_compressed(golden_dir / "fill.npz", **fill_outputs(o))
     np.savez_compressed(golden_dir / "prepost.npz", **prepost_outputs(o))
     for name, H, W, D, kind, seed in MATCHER_CASES:
         out = matcher_outputs(o, H, W, D, kind, seed)

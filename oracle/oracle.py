@@ -198,6 +198,19 @@ class Oracle:
         self._fn("median")(_p(d, _f32p), _p(out, _f32p), W, H, int(k))
         return out
 
+    def fill_the_hole(self, disp, disp_range, occ, mis, fixed=False):
+        """FillTheHole (PostProcessing.h:156) as written.  Returns (disp_out, mismatch_list_after).
+        fixed=True (port only): axes not swapped, invalid = +inf -- not a reference behaviour."""
+        d = np.array(disp, np.float32, order="C", copy=True)
+        row, col = d.shape
+        o = np.ascontiguousarray(occ, np.int32).reshape(-1, 2)
+        cap = max(row * col, len(mis)) + 1
+        m = np.zeros((cap, 2), np.int32)
+        m[: len(mis)] = np.asarray(mis, np.int32).reshape(-1, 2)
+        nm = C.c_int32(len(mis))
+        self._fn("fill_the_hole_fixed" if fixed else "fill_the_hole")(row, col, int(disp_range), _p(d, _f32p), _p(o, _i32p), len(o), _p(m, _i32p), C.byref(nm), cap)
+        return d, m[: nm.value].copy()
+
     def transform_to_show(self, disp):
         """TransformToShow (PostProcessing.h:137)."""
         d = _c(disp, np.float32)

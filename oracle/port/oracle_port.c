@@ -827,3 +827,80 @@ void orc_transform_to_show(const float* disp, int H, int W, uint8_t* out) {
         out[p] = (uint8_t)v;
     }
 }
+
+/* FillTheHole (PostProcessing.h:156-248) as written: width/height are swapped (:158-159), "invalid" is 0xffff (:184,:215)
+ * although the LR check writes +inf, the 8-direction table switches for good at the first target pixel whose y equals
+ * height/2 (:198-200), targets without any hit are filled with 0 (fill_disps is value-initialised, :177,:239-244), and
+ * the third phase replaces the mismatch list by all 0xffff pixels (:179-189).  Never called by the reference's main. */
+static int cmp_float2(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+static void fill_the_hole_impl(int width, int height, float invalid, int dispRange, float* disp, const int32_t* occ, int32_t n_occ,
+                               int32_t* mis, int32_t* n_mis, int32_t mis_capacity) {
+    const float pi = 3.1415926f;
+    const float angle1[8] = {pi, 3 * pi / 4, pi / 2, pi / 4, 0, 7 * pi / 4, 3 * pi / 2, 5 * pi / 4};
+    const float angle2[8] = {pi, 5 * pi / 4, 3 * pi / 2, 7 * pi / 4, 0, pi / 4, pi / 2, 3 * pi / 4};
+    const float* angle = angle1;
+    const int max_len = (int)(1.0 * dispRange);
+    const size_t cap = (size_t)width * height > (size_t)mis_capacity ? (size_t)width * height : (size_t)mis_capacity;
+    int32_t* cur_mis = (int32_t*)malloc((cap + 1) * 2 * sizeof(int32_t));
+    int32_t ncur_mis = *n_mis;
+    memcpy(cur_mis, mis, (size_t)ncur_mis * 2 * sizeof(int32_t));
+    for (int k = 0; k < 3; ++k) {
+        const int32_t* trg = k == 0 ? occ : cur_mis;
+        int32_t ntrg = k == 0 ? n_occ : ncur_mis;
+        if (ntrg == 0) continue;
+        float* fill = (float*)calloc((size_t)((k == 2 ? (size_t)width * height : (size_t)ntrg) + 1), sizeof(float));
+        if (k == 2) {
+            ncur_mis = 0;
+            for (int i = 0; i < height; ++i)
+                for (int j = 0; j < width; ++j)
+                    if (disp[(size_t)i * width + j] == invalid) {
+                        cur_mis[2 * (size_t)ncur_mis] = i;
+                        cur_mis[2 * (size_t)ncur_mis + 1] = j;
+                        ++ncur_mis;
+                    }
+            trg = cur_mis;
+            ntrg = ncur_mis;
+        }
+        for (int32_t n = 0; n < ntrg; ++n) {
+            const int y = trg[2 * n], x = trg[2 * n + 1];
+            if (y == height / 2) angle = angle2;
+            float coll[8];
+            int nc = 0;
+            for (int s = 0; s < 8; ++s) {
+                const float sina = (float)sin(angle[s]), cosa = (float)cos(angle[s]);
+                for (int m = 1; m < max_len; ++m) {
+                    const int yy = (int)lround(y + m * sina), xx = (int)lround(x + m * cosa);
+                    if (yy < 0 || yy >= height || xx < 0 || xx >= width) break;
+                    const float d = disp[(size_t)yy * width + xx];
+                    if (d != invalid) {
+                        coll[nc++] = d;
+                        break;
+                    }
+                }
+            }
+            if (nc == 0) continue;
+            qsort(coll, (size_t)nc, sizeof(float), cmp_float2);
+            fill[n] = k == 0 ? (nc > 1 ? coll[1] : coll[0]) : coll[nc / 2];
+        }
+        for (int32_t n = 0; n < ntrg; ++n) disp[(size_t)trg[2 * n] * width + trg[2 * n + 1]] = fill[n];
+        free(fill);
+    }
+    *n_mis = ncur_mis;
+    for (int32_t k = 0; k < ncur_mis && k < mis_capacity; ++k) {
+        mis[2 * k] = cur_mis[2 * k];
+        mis[2 * k + 1] = cur_mis[2 * k + 1];
+    }
+    free(cur_mis);
+}
+void orc_fill_the_hole(int row, int col, int dispRange, float* disp, const int32_t* occ, int32_t n_occ, int32_t* mis, int32_t* n_mis,
+                       int32_t mis_capacity) {
+    fill_the_hole_impl(row, col, 65535.f, dispRange, disp, occ, n_occ, mis, n_mis, mis_capacity);  /* :158-159 swap */
+}
+/* The evident intent (NOT in the reference, parity unpinned): width = col, height = row, invalid = +inf. */
+void orc_fill_the_hole_fixed(int row, int col, int dispRange, float* disp, const int32_t* occ, int32_t n_occ, int32_t* mis,
+                             int32_t* n_mis, int32_t mis_capacity) {
+    fill_the_hole_impl(col, row, INFINITY, dispRange, disp, occ, n_occ, mis, n_mis, mis_capacity);
+}

@@ -33,6 +33,10 @@ void orc_remove_speckles_inf(float* disp, int W, int H, int diff, unsigned min_a
 void orc_remove_speckles(float* disp, int W, int H, int diff, unsigned min_area, int invalid_val);
 void orc_median(const float* in, float* out, int W, int H, int k);
 void orc_transform_to_show(const float* disp, int H, int W, uint8_t* out);
+void orc_fill_the_hole_fixed(int row, int col, int dispRange, float* disp, const int32_t* occ, int32_t n_occ, int32_t* mis,
+                             int32_t* n_mis, int32_t mis_capacity);
+void orc_fill_the_hole(int row, int col, int dispRange, float* disp, const int32_t* occ, int32_t n_occ, int32_t* mis, int32_t* n_mis,
+                       int32_t mis_capacity);
 int orc_cross_aggregate(const uint8_t* bgrL, const uint8_t* bgrR, const float* cost_init, int W, int H, int D, int L1,
                         int L2, int t1, int t2, int iters, float* cost_out, uint8_t* arms, uint16_t* sup0,
                         uint16_t* sup1);

@@ -184,6 +184,17 @@ void ref_remove_speckles(float* disp, int W, int H, int diff, unsigned min_area,
     rns_adc::RemoveSpeckles(disp, W, H, diff, min_area, invalid_val);
 }
 void ref_median(const float* in, float* out, int W, int H, int k) { rns_adc::MedianFilter(in, out, W, H, k); }
+// FillTheHole (PostProcessing.h:156-248), exactly as written (it swaps width/height and tests 0xffff; never called by the
+// reference's main).  occ / mis: (row, col) pairs in, mis is overwritten by the third phase like the reference's vector.
+void ref_fill_the_hole(int row, int col, int dispRange, float* disp, const int32_t* occ, int32_t n_occ, int32_t* mis, int32_t* n_mis,
+                       int32_t mis_capacity) {
+    std::vector<std::pair<int, int>> o, m;
+    for (int k = 0; k < n_occ; ++k) o.emplace_back(occ[2 * k], occ[2 * k + 1]);
+    for (int k = 0; k < *n_mis; ++k) m.emplace_back(mis[2 * k], mis[2 * k + 1]);
+    rns_adc::FillTheHole(row, col, dispRange, disp, o, m);
+    *n_mis = (int32_t)m.size();
+    for (size_t k = 0; k < m.size() && (int32_t)k < mis_capacity; ++k) { mis[2 * k] = m[k].first; mis[2 * k + 1] = m[k].second; }
+}
 // TransformToShow (PostProcessing.h:137): float disparity -> 8-bit display image
 void ref_transform_to_show(const float* disp, int H, int W, uint8_t* out) {
     cv::Mat t(H, W, cv::CV_8UC1, out);

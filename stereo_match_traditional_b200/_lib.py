@@ -53,6 +53,7 @@ SIGNATURES = {
     "smt_create": (_i, [_i, _vp, C.POINTER(_vp)]),
     "smt_destroy": (None, [_vp]),
     "smt_sync": (_i, [_vp]),
+    "smt_get_stream": (_vp, [_vp]),
     "smt_last_error_string": (C.c_char_p, [_vp]),
     "smt_status_string": (C.c_char_p, [_i]),
     "smt_kernel_launches": (C.c_uint64, [_vp]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "smt_lrcheck_and": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _i32p, _vp, _i32p, _i]),
     "smt_remove_speckles": (_i, [_vp, _vp, _i, _i, _i, C.c_uint32, _i, _i]),
     "smt_median": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
+    "smt_fill_the_hole": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i]),
     "smt_sad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     "smt_ncc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
     "smt_asw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _i, _i, _vp, _i]),

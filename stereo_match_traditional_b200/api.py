@@ -49,6 +49,7 @@ class _Args:
         self.engine = engine
         self.device = any(_is_torch(a) and a.is_cuda for a in inputs if a is not None)
         self.keep = []
+        engine._device_call = self.device   # the next library call is ordered against torch's current stream
 
     @property
     def space(self) -> int:
@@ -96,11 +97,46 @@ class _Args:
         return a, C.c_void_p(a.ctypes.data)
 
 
+class _OrderedLib:
+    """The ctypes library as the Engine's methods see it.  A call that takes torch CUDA tensors runs on the context's
+    stream, which is in general not the stream torch is using: the call is queued behind the work torch's current stream
+    already holds (the producers of the inputs) and torch's current stream is then made to wait for it (the consumers of the
+    outputs, and the caching allocator's reuse of freed blocks).  Everything else is passed through untouched."""
+
+    def __init__(self, engine: "Engine", lib):
+        self._engine, self._lib = engine, lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        eng = self._engine
+
+        def call(*args):
+            if not eng._device_call:      # set per method call by _Args; stays set for every library call of that method
+                return fn(*args)
+            import torch
+
+            cur = torch.cuda.current_stream(eng.device)
+            ext = eng.torch_stream
+            if cur.cuda_stream == ext.cuda_stream:
+                return fn(*args)
+            ext.wait_stream(cur)
+            try:
+                return fn(*args)
+            finally:
+                cur.wait_stream(ext)
+
+        setattr(self, name, call)
+        return call
+
+
 class Engine:
     """One ``smt_ctx``: a device, a stream, a cached device workspace."""
 
     def __init__(self, device: int = 0, stream: Optional[int] = None):
-        self.lib = _lib.load()
+        self._device_call = False
+        self._torch_stream = None
+        self._raw = _lib.load()
+        self.lib = _OrderedLib(self, self._raw)
         self.device = int(device)
         h = C.c_void_p()
         st = self.lib.smt_create(self.device, C.c_void_p(stream) if stream else None, C.byref(h))
@@ -112,7 +148,9 @@ class Engine:
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "h", None):
-            self.lib.smt_destroy(self.h)
+            self._device_call = False
+            self._torch_stream = None
+            self._raw.smt_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -133,6 +171,15 @@ class Engine:
 
     def sync(self):
         self._ck(self.lib.smt_sync(self.h))
+
+    @property
+    def torch_stream(self):
+        """The context's stream as a torch stream (for wait_stream / events)."""
+        if self._torch_stream is None:
+            import torch
+
+            self._torch_stream = torch.cuda.ExternalStream(int(self._raw.smt_get_stream(self.h)), device=f"cuda:{self.device}")
+        return self._torch_stream
 
     def trim(self):
         self._ck(self.lib.smt_trim(self.h))
@@ -300,6 +347,25 @@ class Engine:
         d, pd = a.out((H, W), np.float32, init=disp)
         self._ck(self.lib.smt_remove_speckles(self.h, pd, W, H, int(diff), int(min_area), int(invalid), a.space))
         return d
+
+    def fill_the_hole(self, disp, disp_range, occ, mis, fixed: bool = False):
+        """FillTheHole (PostProcessing.h:156).  As written (default): list entries (y, x) address disp.flat[y*rows + x]
+        (the function swaps the axes), invalid = 65535.  fixed=True: entries are (row, col), invalid = +inf.
+        Returns (disp_out, mismatch_list_after)."""
+        a = _Args(self, disp)
+        H, W = disp.shape
+        d, pd = a.out((H, W), np.float32, init=disp)
+        occ = np.ascontiguousarray(np.asarray(occ.cpu() if hasattr(occ, "cpu") else occ, np.int32).reshape(-1, 2))
+        mis = np.asarray(mis.cpu() if hasattr(mis, "cpu") else mis, np.int32).reshape(-1, 2)
+        if len(mis) > H * W or len(occ) > H * W:
+            raise ValueError("list longer than the image")
+        m0 = np.zeros((H * W, 2), np.int32)
+        m0[: len(mis)] = mis
+        po = a.inp(occ, np.int32) if len(occ) else None
+        m, pm = a.out((H * W, 2), np.int32, init=m0)
+        nm = C.c_int32(len(mis))
+        self._ck(self.lib.smt_fill_the_hole(self.h, pd, H, W, int(disp_range), po, len(occ), pm, C.byref(nm), 1 if fixed else 0, a.space))
+        return d, m[: nm.value]
 
     def median(self, disp, k=3):
         a = _Args(self, disp)

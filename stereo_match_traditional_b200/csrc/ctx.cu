@@ -141,6 +141,8 @@ smt_status_t smt_sync(smt_ctx* ctx) {
     return SMT_OK;
 }
 
+void* smt_get_stream(const smt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 const char* smt_last_error_string(const smt_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 
 uint64_t smt_kernel_launches(const smt_ctx* ctx) { return ctx ? ctx->launches : 0; }

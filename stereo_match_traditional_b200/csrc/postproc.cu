@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) lr_apply_kernel(const unsigned char* __re
     }
     if (variant_and) {
         last[p] = k ? 0.f : dl_orig[p];  // :56,:60,:65
-    } else if (k) {
+    } else if (k && dl_inout) {
         dl_inout[p] = INFINITY;  // :125,:130 (already +inf inputs stay +inf)
     }
 }
@@ -345,6 +345,158 @@ smt_status_t k_median(smt_ctx* ctx, const float* in, float* out, int W, int H, i
     return SMT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- hole filling
+// FillTheHole (AD-CensusV1/PostProcessing.h:156-248) exactly as written; the function is never called by the reference's
+// main and is kept for API completeness.  What "as written" means:
+//  * width = row and height = col (:158-159): pixel (y, x) of a list addresses disp[y*row + x], y < col, x < row;
+//  * "invalid" is the value 0xffff (:184, :215), not the +inf LeftRightConsistency writes, so +inf is collected as valid;
+//  * the direction table switches from angle1 to angle2 at the first target (in list order) whose y equals height/2 and
+//    never switches back, also across the three phases (:198-200) -> `first` / `switched` below;
+//  * a target without any hit is filled with 0 (value-initialised fill_disps, :177, :239-244);
+//  * a phase reads the map of the previous phase only (fills are written after the whole list was visited, :239), so a
+//    phase is one parallel kernel; duplicates in a list resolve to the LAST entry like the sequential write loop;
+//  * phase 3 replaces the mismatch list by all 0xffff pixels in raster order (:179-189) and is skipped when the mismatch
+//    list was empty (:175).  The reference sizes fill_disps before that replacement, so it overflows the heap when
+//    there are more 0xffff pixels than mismatches; here that case simply fills all of them.
+struct FillDirs {
+    float sina[2][8], cosa[2][8];
+};
+
+__global__ void __launch_bounds__(256) fill_scan_kernel(const int* __restrict__ trg, int ntrg, int width, int height,
+                                                        int* __restrict__ first, int* __restrict__ owner, int* __restrict__ bad) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ntrg) return;
+    const int y = trg[2 * n], x = trg[2 * n + 1];
+    if (y < 0 || y >= height || x < 0 || x >= width) {
+        *bad = 1;
+        return;
+    }
+    if (y == height / 2) atomicMin(first, n);
+    atomicMax(&owner[(size_t)y * width + x], n);
+}
+
+__global__ void __launch_bounds__(256) fill_collect_kernel(const float* __restrict__ disp, const int* __restrict__ trg, int ntrg,
+                                                           int width, int height, int max_len, int phase, float invalid, FillDirs dirs,
+                                                           const int* __restrict__ first, const int* __restrict__ switched,
+                                                           float* __restrict__ fill) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ntrg) return;
+    const int y = trg[2 * n], x = trg[2 * n + 1];
+    const int tab = (*switched || n >= *first) ? 1 : 0;
+    float coll[8];
+    int nc = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const float sina = dirs.sina[tab][s], cosa = dirs.cosa[tab][s];
+        for (int m = 1; m < max_len; ++m) {
+            const int yy = (int)lroundf(__fadd_rn((float)y, __fmul_rn((float)m, sina)));  // :209
+            const int xx = (int)lroundf(__fadd_rn((float)x, __fmul_rn((float)m, cosa)));
+            if (yy < 0 || yy >= height || xx < 0 || xx >= width) break;
+            const float d = disp[(size_t)yy * width + xx];
+            if (d != invalid) {
+                // insertion into the sorted prefix (std::sort of <= 8 values, :226)
+                int k = nc++;
+#pragma unroll
+                for (int q = 7; q > 0; --q)
+                    if (q <= k && coll[q - 1] > d) {
+                        coll[q] = coll[q - 1];
+                        k = q - 1;
+                    }
+                coll[k] = d;
+                break;
+            }
+        }
+    }
+    float v = 0.f;
+    if (nc) v = phase == 0 ? coll[nc > 1 ? 1 : 0] : coll[nc / 2];  // :230-241
+    fill[n] = v;
+}
+
+__global__ void __launch_bounds__(256) fill_write_kernel(float* __restrict__ disp, const int* __restrict__ trg, int ntrg, int width,
+                                                         const float* __restrict__ fill, int* __restrict__ owner,
+                                                         int* __restrict__ first, int* __restrict__ switched) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0 && *first != 0x7fffffff) *switched = 1;
+    if (n >= ntrg) return;
+    const size_t p = (size_t)trg[2 * n] * width + trg[2 * n + 1];
+    if (owner[p] == n) {
+        disp[p] = fill[n];
+        owner[p] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_mark_kernel(const float* __restrict__ disp, size_t n, float invalid,
+                                                        unsigned char* __restrict__ cls) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) cls[p] = disp[p] == invalid ? 2 : 0;
+}
+
+// variant SMT_FILL_FIXED: what the function evidently means -- width = col, height = row (list entries are the (row, col)
+// pairs LeftRightConsistency emits), invalid = +inf (what LeftRightConsistency writes); everything else unchanged.
+smt_status_t k_fill_the_hole(smt_ctx* ctx, float* disp, int row, int col, int disp_range, const int32_t* occ, int n_occ, int32_t* mis,
+                             int* n_mis_inout, int variant) {
+    StageTimer t(ctx, ST_POST);
+    const bool fixed = variant == SMT_FILL_FIXED;
+    const int width = fixed ? col : row, height = fixed ? row : col;
+    const float invalid = fixed ? INFINITY : 65535.f;
+    const size_t n = (size_t)row * col;
+    FillDirs dirs;
+    {
+        const float pi = 3.1415926f;  // :164-166, evaluated in float like the reference's initialisers
+        const float a1[8] = {pi, 3 * pi / 4, pi / 2, pi / 4, 0, 7 * pi / 4, 3 * pi / 2, 5 * pi / 4};
+        const float a2[8] = {pi, 5 * pi / 4, 3 * pi / 2, 7 * pi / 4, 0, pi / 4, pi / 2, 3 * pi / 4};
+        for (int s = 0; s < 8; ++s) {
+            dirs.sina[0][s] = float(sin(a1[s]));  // :206-207, host libm like the LUTs of the cost kernel
+            dirs.cosa[0][s] = float(cos(a1[s]));
+            dirs.sina[1][s] = float(sin(a2[s]));
+            dirs.cosa[1][s] = float(cos(a2[s]));
+        }
+    }
+    SMT_ALLOC(ctx, owner, n * sizeof(int));
+    SMT_ALLOC(ctx, fill, n * sizeof(float));
+    SMT_ALLOC(ctx, st, 4 * sizeof(int));  // first, switched, bad, pad
+    int* first = st.as<int>();
+    int* switched = first + 1;
+    int* bad = first + 2;
+    SMT_CUDA(ctx, cudaMemsetAsync(owner.p, 0xff, n * sizeof(int), ctx->stream));
+    SMT_CUDA(ctx, cudaMemsetAsync(st.p, 0, 4 * sizeof(int), ctx->stream));
+    int n_mis = *n_mis_inout;
+    for (int k = 0; k < 3; ++k) {
+        const int32_t* trg = k == 0 ? occ : mis;
+        int ntrg = k == 0 ? n_occ : n_mis;
+        if (ntrg == 0) continue;  // :175 (phase 3 looks at the OLD mismatch list)
+        if (k == 2) {
+            const int nb = (int)cdiv((long long)n, 256);
+            SMT_ALLOC(ctx, cls, n);
+            SMT_ALLOC(ctx, bc, (size_t)nb * 2 * sizeof(int));
+            SMT_ALLOC(ctx, counts, 2 * sizeof(int));
+            SMT_LAUNCH(ctx, fill_mark_kernel, nb, 256, 0, disp, n, invalid, cls.as<unsigned char>());
+            SMT_LAUNCH(ctx, lr_count_kernel, nb, 256, 0, cls.as<unsigned char>(), n, bc.as<int>());
+            SMT_LAUNCH(ctx, lr_scan_kernel, 1, 1024, 0, bc.as<int>(), nb, counts.as<int>());
+            SMT_LAUNCH(ctx, lr_apply_kernel, nb, 256, 0, cls.as<unsigned char>(), bc.as<int>(), width, height, 0, (float*)nullptr,
+                       (const float*)nullptr, (float*)nullptr, (int*)nullptr, mis);
+            SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, counts.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ntrg = n_mis = ctx->h_pinned[1];
+            if (ntrg == 0) break;
+        }
+        const int nbt = (int)cdiv(ntrg, 256);
+        const int init_first = 0x7fffffff;
+        SMT_CUDA(ctx, cudaMemcpyAsync(first, &init_first, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        SMT_LAUNCH(ctx, fill_scan_kernel, nbt, 256, 0, trg, ntrg, width, height, first, owner.as<int>(), bad);
+        SMT_LAUNCH(ctx, fill_collect_kernel, nbt, 256, 0, disp, trg, ntrg, width, height, disp_range, k, invalid, dirs, first, switched,
+                   fill.as<float>());
+        SMT_LAUNCH(ctx, fill_write_kernel, nbt, 256, 0, disp, trg, ntrg, width, fill.as<float>(), owner.as<int>(), first, switched);
+    }
+    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned[0])
+        return smt_fail(ctx, SMT_ERR_INVALID_ARG,
+                        "smt_fill_the_hole: list entry outside the frame (as written: y < col, x < row, PostProcessing.h:158-159)");
+    *n_mis_inout = n_mis;
+    return SMT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- C ABI
 static smt_status_t lrcheck_common(smt_ctx* ctx, float* dl_inout, const float* dl_const, const float* dr, float* last, int cols,
                                    int rows, float gate, bool variant_and, int32_t* occ, int32_t* n_occ, int32_t* mis,
@@ -398,6 +550,26 @@ smt_status_t smt_remove_speckles(smt_ctx* ctx, float* disp, int32_t cols, int32_
     float* d = ms.out(disp, (size_t)rows * cols, true);
     SMT_TRY(ms.check());
     SMT_TRY(k_remove_speckles(ctx, d, cols, rows, diff, min_area, invalid_val));
+    return ms.finish();
+}
+
+smt_status_t smt_fill_the_hole(smt_ctx* ctx, float* disp, int32_t row, int32_t col, int32_t disp_range, const int32_t* occ,
+                               int32_t n_occ, int32_t* mis, int32_t* n_mis, int32_t variant, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, disp && row > 0 && col > 0 && n_occ >= 0 && n_mis && *n_mis >= 0 && (occ || n_occ == 0) && mis &&
+                         (variant == SMT_FILL_AS_WRITTEN || variant == SMT_FILL_FIXED),
+                SMT_ERR_INVALID_ARG, "smt_fill_the_hole: bad argument");
+    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)row * col;
+    SMT_REQUIRE(ctx, (size_t)n_occ <= n && (size_t)*n_mis <= n, SMT_ERR_INVALID_ARG, "smt_fill_the_hole: list longer than the image");
+    Marshal ms(ctx, space);
+    float* d = ms.out(disp, n, true);
+    const int32_t* docc = n_occ ? ms.in(occ, 2 * (size_t)n_occ) : nullptr;
+    int32_t* dmis = ms.out(mis, 2 * n, true);
+    SMT_TRY(ms.check());
+    int nm = *n_mis;
+    SMT_TRY(k_fill_the_hole(ctx, d, row, col, disp_range, docc, n_occ, dmis, &nm, variant));
+    *n_mis = nm;
     return ms.finish();
 }
 

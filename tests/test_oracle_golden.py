@@ -83,3 +83,20 @@ def test_sad_optimal_disparity_quirks(oracle_port):
 def test_port_transform_to_show_matches_reference_golden(oracle_port):
     z = np.load(GOLDEN / "prepost.npz")
     assert np.array_equal(oracle_port.transform_to_show(z["in_disp"]), z["show"])
+
+
+def test_port_fill_the_hole_matches_reference_golden(oracle_port):
+    """FillTheHole as written (PostProcessing.h:156): fixtures from the compiled reference (oracle/make_golden_matchers.py)."""
+    from oracle.make_golden_matchers import FILL_CASES, fill_inputs
+
+    z = np.load(GOLDEN / "fill.npz")
+    for H, W, D, seed in FILL_CASES:
+        d, occ, mis = fill_inputs(H, W, D, seed)
+        f, m = oracle_port.fill_the_hole(d, D, occ, mis)
+        assert np.array_equal(f, z[f"fill_{H}x{W}x{D}"]) and np.array_equal(m, z[f"mis_{H}x{W}x{D}"])
+    # phase 3 is skipped when the mismatch list is empty (:175), and nothing happens with both lists empty
+    d, occ, _ = fill_inputs(20, 28, 8, 3)
+    f, m = oracle_port.fill_the_hole(d, 8, occ, np.zeros((0, 2), np.int32))
+    assert len(m) == 0 and (f == 65535).sum() > 0
+    f, _ = oracle_port.fill_the_hole(d, 8, np.zeros((0, 2), np.int32), np.zeros((0, 2), np.int32))
+    assert np.array_equal(f, d)
