@@ -23,9 +23,18 @@ namespace {
 
 constexpr int SEQ_R = 96;     // ring entries: three 32-position chunks (span needed: 70 + SEQ_G)
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
-constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane).  16 with SEQ_R = 80 and 5-warp blocks (10 warps/SM,
-                              // ~100 registers) was measured 3 % slower, and overlapping the other view's scanline on a
-                              // second stream gained nothing: the passes are limited by the memory system, not by occupancy
+constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
+// Measured on B200 at 1080p x 256 (ms per pass; 1.30 as shipped), see DESIGN.md 7:
+//   no loads and no stores 0.96, no stores 1.09, no loads 1.03: the walk is neither purely memory- nor issue-bound;
+//   16-position chunks, 80-entry ring, 10 warps/SM: 1.34;  one chunk in flight instead of two (127 registers): 1.33;
+//   16 warps/SM (timing-only run with a truncated ring): 1.22;  descriptor/ring reads software-pipelined by hand: 1.36
+//   (ncu: short-scoreboard stalls 19 -> 12 %, but the larger code raised instruction-cache stalls 7 -> 14 %);
+//   compile-time position step for horizontal passes (-27 % instructions in those passes): 1.29;
+//   arm words / support counts fetched two chunks ahead instead of one (6 % of the stall samples sit on their first use): 1.31.
+#ifndef SMT_SEQ_AHEAD
+#define SMT_SEQ_AHEAD 2
+#endif
+constexpr int SEQ_AHEAD = SMT_SEQ_AHEAD;  // chunks of input in flight per warp (register buffers = SEQ_AHEAD + 1)
 constexpr int SEQ_G = 8;      // outputs are emitted in groups of SEQ_G (ring span needed: 70 + SEQ_G <= SEQ_R)
 
 struct pair2 {
@@ -78,20 +87,21 @@ __device__ __forceinline__ float key2f_(unsigned k) { return __uint_as_float(k ^
 
 // WTA: instead of storing the pass output, reduce it over the warp's 32 disparities (first minimum) and store one
 // (value, d) pair per position and d-chunk; wta_reduce_kernel finishes the arg-min over the chunks.
-template <bool NONNEG, bool HAS_SUP, bool EDGE, bool WTA>
+template <bool NONNEG, bool HAS_SUP, bool EDGE, bool WTA, int CSTEP = 0>
 __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
-                                          const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
+                                          const float* __restrict__ src_next, float* __restrict__ dst_first, long long step_rt,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
                                           float2* __restrict__ wta_first, long long wta_step, int d) {
-    // ---- loads of chunk tb + 2*32 (consumed two chunks later: with 8 warps per SM one chunk of loads in flight per
+    const long long step = CSTEP ? (long long)CSTEP : step_rt;
+    // ---- loads of chunk tb + SEQ_AHEAD*32 (consumed SEQ_AHEAD chunks later: with 8 warps per SM one chunk of loads in flight per
     // warp does not cover the DRAM latency -- ncu showed 35 % of all stall samples on the first use of a chunk)
     {
         const float* p = src_next;
 #pragma unroll
         for (int k = 0; k < SEQ_CH; ++k) {
             if (EDGE)
-                vload[k] = (tb + 2 * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+                vload[k] = (tb + SEQ_AHEAD * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
             else
                 vload[k] = __ldcs(p);
             p += step;
@@ -164,14 +174,16 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 constexpr int SEQ_WARPS = 8;  // the 8 warps of a block walk the d-chunks of the same line(s): 1 KB contiguous per pixel
 constexpr int SEQ_SMEM_PER_WARP = SEQ_R * 256 + SEQ_CH * (int)sizeof(Desc);
 
-template <bool NONNEG, bool HAS_SUP, bool WTA>
+template <bool NONNEG, bool HAS_SUP, bool WTA, int CSTEP = 0>
 __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
                                                      int D, int horiz, float bias, float2* __restrict__ wta_partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
-    Desc* s_desc = reinterpret_cast<Desc*>(s_ring + SEQ_R * 256);
+    // a separate object, so that the compiler may move descriptor loads across ring stores
+    __shared__ Desc s_desc_all[SEQ_WARPS][SEQ_CH];
+    Desc* s_desc = s_desc_all[warp];
     const int nchunk = (D + 31) >> 5;
     const long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
     const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
@@ -182,18 +194,18 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
     const bool full = chunk * 32 + 32 <= D;  // every lane active: the interior path needs no lane predicate
     const long long pstride = horiz ? 1 : (long long)W;
     const long long pbase = horiz ? (long long)line * W : (long long)line;
-    const long long step = pstride * D;
+    const long long step = CSTEP ? (long long)CSTEP : pstride * D;
     const float* src = in + pbase * D + (act ? d : 0);
     float* dst = out + pbase * D + (act ? d : 0);
     unsigned char* ring_col = s_ring + lane * 8;
 
     pair2 acc{NONNEG ? bias : 0.f, 0.f};
     // three register buffers rotate: while chunk o is consumed, chunks o+1 and o+2 are in flight (8 KB per warp)
-    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
+    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_AHEAD == 2 ? SEQ_CH : 1];
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
         va[k] = (k < len && act) ? __ldcs(src + step * k) : 0.f;
-        vb[k] = (SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
+        if (SEQ_AHEAD == 2) vb[k] = (SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
     }
 
     Prefetched pre{0u, 1};  // chunk 0 outputs positions -35..-4: nothing to fetch; its call fetches chunk 1's
@@ -202,25 +214,30 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
 #define SMT_SEQ_STEP(USE, LOAD)                                                                                               \
     if (o < nouter) {                                                                                                         \
         const int tb = o * SEQ_CH;                                                                                            \
-        const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                               \
+        const float* src_next = src + step * (tb + SEQ_AHEAD * SEQ_CH);                                                       \
         float* dst_first = dst + step * (tb - SEQ_LOOK);                                                                      \
         float2* wta_first = WTA ? wta_partial + (pbase + pstride * (tb - SEQ_LOOK)) * nchunk + chunk : nullptr;               \
         const long long wta_step = pstride * nchunk;                                                                          \
         /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
-        if (full && tb - SEQ_LOOK >= 0 && tb + 3 * SEQ_CH <= len)                                                             \
-            seq_chunk<NONNEG, HAS_SUP, false, WTA>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,       \
+        if (full && tb - SEQ_LOOK >= 0 && tb + (SEQ_AHEAD + 1) * SEQ_CH <= len)                                               \
+            seq_chunk<NONNEG, HAS_SUP, false, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,       \
                                                    pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,               \
                                                    wta_step, chunk * 32);                                                     \
         else                                                                                                                  \
-            seq_chunk<NONNEG, HAS_SUP, true, WTA>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,        \
+            seq_chunk<NONNEG, HAS_SUP, true, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,        \
                                                   pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,                \
                                                   wta_step, chunk * 32);                                                      \
         ++o;                                                                                                                  \
     }
     for (int o = 0; o < nouter;) {
+#if SMT_SEQ_AHEAD == 2
         SMT_SEQ_STEP(va, vc)
         SMT_SEQ_STEP(vb, va)
         SMT_SEQ_STEP(vc, vb)
+#else
+        SMT_SEQ_STEP(va, vb)
+        SMT_SEQ_STEP(vb, va)
+#endif
     }
 #undef SMT_SEQ_STEP
 }
@@ -410,6 +427,18 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
         attr_set = true;
     }
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    // horizontal walk of a 256-disparity volume (the benchmark shape): the position step is a compile-time constant, so
+    // the 32 loads and 32 stores of a chunk use immediate offsets from one base register (-27 % instructions, +1.3 %)
+    if constexpr (NONNEG && !WTA) if (horiz && D == 256) {
+        static bool attr2 = false;
+        if (!attr2) {
+            SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr2 = true;
+        }
+        SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
+                   horiz, bias, wta_partial);
+        return SMT_OK;
+    }
     SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
                bias, wta_partial);
     return SMT_OK;
