@@ -57,6 +57,55 @@ __global__ void __launch_bounds__(128) cross_arms_kernel(const uint8_t* __restri
     arms[(size_t)y * W + x] = a;
 }
 
+// Packed variant for thresholds 1..128 (the reference's 20 and 6): one 32-bit word per pixel (B, G, R, 0), the three
+// channel differences in one VABSDIFF4, "some byte >= t" as the carry-free SWAR test ((d + (128 - t)*0x01010101) | d) & 0x80808080
+// (bytes of d + (128 - t) cannot carry: 255 + 127 < 512 only matters per byte when d >= 128, and then the `| d` term
+// already has the top bit set -- so the sum is formed on the low 7 bits only).
+__global__ void __launch_bounds__(256) pack_bgr_kernel(const uint8_t* __restrict__ bgr, size_t n, uint32_t* __restrict__ out) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[k] = (uint32_t)bgr[3 * k] | ((uint32_t)bgr[3 * k + 1] << 8) | ((uint32_t)bgr[3 * k + 2] << 16);
+}
+
+__device__ __forceinline__ bool any_byte_ge(unsigned d, unsigned bias) {  // bias = (128 - t) * 0x01010101, 1 <= t <= 128
+    return ((((d & 0x7f7f7f7fu) + bias) | d) & 0x80808080u) != 0u;
+}
+
+__device__ __forceinline__ int walk_arm_packed(const uint32_t* __restrict__ p0, long long step, int room, int Lmax, int L2,
+                                               unsigned bias1, unsigned bias2) {
+    const unsigned c0 = *p0;
+    unsigned cl = c0;
+    int arm = 0;
+    const uint32_t* p = p0 + step;
+    const int lim = min(Lmax, room);  // border (:154-163)
+    for (int n = 0; n < lim; ++n) {
+        const unsigned c = *p;
+        const unsigned d0 = __vabsdiffu4(c, c0);
+        if (any_byte_ge(d0, bias1)) break;                               // :169-172
+        if (n > 0 && any_byte_ge(__vabsdiffu4(c, cl), bias1)) break;     // :175-180
+        if (n + 1 > L2 && any_byte_ge(d0, bias2)) break;                 // :183-187
+        ++arm;
+        cl = c;
+        p += step;
+    }
+    return arm;
+}
+
+__global__ void __launch_bounds__(128) cross_arms_packed_kernel(const uint32_t* __restrict__ pix, int H, int W, int L1, int L2,
+                                                                unsigned bias1, unsigned bias2, uchar4* __restrict__ arms) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const int Lmax = min(L1, 255);
+    const uint32_t* p0 = pix + (size_t)y * W + x;
+    uchar4 a;
+    a.x = (unsigned char)walk_arm_packed(p0, -1, x, Lmax, L2, bias1, bias2);
+    a.y = (unsigned char)walk_arm_packed(p0, 1, W - 1 - x, Lmax, L2, bias1, bias2);
+    a.z = (unsigned char)walk_arm_packed(p0, -(long long)W, y, Lmax, L2, bias1, bias2);
+    a.w = (unsigned char)walk_arm_packed(p0, (long long)W, H - 1 - y, Lmax, L2, bias1, bias2);
+    arms[(size_t)y * W + x] = a;
+}
+
 // sup_hfirst(y,x) = sum_{t=-top..bottom} (left+right+1)(y+t,x);  sup_vfirst(y,x) = sum_{t=-left..right} (top+bottom+1)(y,x+t)
 // (cross_aggregator.cpp:271-325; uint16 storage as in the reference).
 __global__ void __launch_bounds__(128) support_count_kernel(const uchar4* __restrict__ arms, int H, int W,
@@ -82,7 +131,15 @@ smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1
                           uint16_t* sup0, uint16_t* sup1) {
     StageTimer t(ctx, ST_ARMS);
     dim3 grid(cdiv(W, 128), H);
-    SMT_LAUNCH(ctx, cross_arms_kernel, grid, 128, 0, bgr, H, W, L1, L2, t1, t2, reinterpret_cast<uchar4*>(arms));
+    if (t1 >= 1 && t1 <= 128 && t2 >= 1 && t2 <= 128) {
+        const size_t npix = (size_t)H * W;
+        SMT_ALLOC(ctx, packed, npix * sizeof(uint32_t));
+        SMT_LAUNCH(ctx, pack_bgr_kernel, cdiv((long long)npix, 256), 256, 0, bgr, npix, packed.as<uint32_t>());
+        SMT_LAUNCH(ctx, cross_arms_packed_kernel, grid, 128, 0, packed.as<uint32_t>(), H, W, L1, L2, (unsigned)(128 - t1) * 0x01010101u,
+                   (unsigned)(128 - t2) * 0x01010101u, reinterpret_cast<uchar4*>(arms));
+    } else {
+        SMT_LAUNCH(ctx, cross_arms_kernel, grid, 128, 0, bgr, H, W, L1, L2, t1, t2, reinterpret_cast<uchar4*>(arms));
+    }
     if (sup0 || sup1)
         SMT_LAUNCH(ctx, support_count_kernel, grid, 128, 0, reinterpret_cast<const uchar4*>(arms), H, W, sup0, sup1);
     return SMT_OK;

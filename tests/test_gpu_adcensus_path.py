@@ -186,3 +186,22 @@ def test_pipeline_fast_disparities(engine, oracle, H, W, D, kind, seed):
         assert np.abs(got[n] - ref[n]).max() <= 1, n
     same = (got["disp"] == ref["disp"]).mean()
     assert same >= 0.999, f"disp: {same:.4%}"
+
+
+@pytest.mark.parametrize("t1,t2,L1,L2", [(20, 6, 34, 17), (1, 1, 34, 17), (128, 128, 34, 17), (127, 3, 20, 5), (129, 6, 34, 17),
+                                         (20, 200, 34, 17), (255, 255, 34, 0), (60, 30, 9, 34)])
+def test_cross_arms_threshold_sweep(engine, oracle, t1, t2, L1, L2):
+    """BuildArms (cross_aggregator.cpp:135-225) over the whole threshold range: 1..128 runs the packed SIMD walk, larger
+    thresholds the scalar one; high-contrast noise makes every rule (tau1 vs centre, vs predecessor, tau2 beyond L2) fire."""
+    H, W = 48, 90
+    rng = np.random.default_rng(t1 * 7 + t2)
+    base = rng.integers(0, 256, (H, W, 3)).astype(np.int32)
+    smooth = (np.add.outer(np.arange(H), np.arange(W))[..., None] * np.array([1, 2, 3]) % 256).astype(np.int32)
+    mix = np.where(rng.random((H, W, 1)) < 0.15, base, smooth + rng.integers(-3, 4, (H, W, 3)))
+    bgr = np.clip(mix, 0, 255).astype(np.uint8)
+    cost = np.zeros((H, W, 1), np.float32)
+    ref = oracle.cross_aggregate(bgr, bgr, cost, L1=L1, L2=L2, t1=t1, t2=t2, iters=1)
+    got = engine.cross_arms(bgr, L1, L2, t1, t2)
+    assert np.array_equal(got["arms"], ref["arms"])
+    assert np.array_equal(got["sup0"], ref["sup0"]) and np.array_equal(got["sup1"], ref["sup1"])
+    assert ref["arms"].max() > 0
