@@ -205,3 +205,24 @@ def test_cross_arms_threshold_sweep(engine, oracle, t1, t2, L1, L2):
     assert np.array_equal(got["arms"], ref["arms"])
     assert np.array_equal(got["sup0"], ref["sup0"]) and np.array_equal(got["sup1"], ref["sup1"])
     assert ref["arms"].max() > 0
+
+
+DEGENERATE = [(9, 9, 1), (10, 12, 3), (7, 20, 4), (12, 300, 5), (200, 12, 9), (3, 40, 6), (20, 8, 12), (16, 33, 33), (35, 36, 65),
+              (1, 50, 4), (50, 1, 1), (2, 2, 2), (71, 73, 31), (36, 140, 97)]
+
+
+@pytest.mark.parametrize("H,W,D", DEGENERATE, ids=lambda v: str(v))
+def test_pipeline_degenerate_shapes(engine, oracle, H, W, D):
+    """Images smaller than the census window, than one arm, than one 32-position chunk, D = 1, D > W, D not a multiple of
+    32: the reference-order pipeline stays bit-exact, the fast one within the disparity bar."""
+    from stereo_match_traditional_b200.api import SUM_FAST
+
+    p = make_pair(H, W, D, 100 + H + W, "noise")
+    ref = oracle_pfull(oracle, p, D)
+    names = ("disp", "left_raw", "right_raw", "lrc")
+    got = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=names)
+    for n in names:
+        assert np.array_equal(got[n], ref[n], equal_nan=True), n
+    fast = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=names, sum_mode=SUM_FAST)
+    for n in ("left_raw", "right_raw"):
+        assert (fast[n] == ref[n]).mean() >= 0.99 and np.abs(fast[n] - ref[n]).max() <= 1, n   # few pixels: 1 % = a handful
