@@ -17,11 +17,27 @@
 // bias keeps the FastTwoSum error term exact), general TwoSum pair otherwise; window sums are exact to ~2^-46 and
 // rounded once.  The division by the support count is the correctly rounded quotient (Markstein's residual step on the
 // correctly rounded reciprocal), i.e. the same bits as the reference's IEEE `cost / count` (:389).
+#include <string>
+
 #include "common.cuh"
 
+// Development switches for the ablation runs quoted in DESIGN.md (all off in the product build):
+//   -DSMT_ABL_NOLOAD   volume loads replaced by a runtime constant      -DSMT_ABL_NOSTORE  volume stores predicated off
+//   -DSMT_ABL_OCC16    timing only (WRONG results): 32-entry ring and one chunk in flight, so that 16 warps fit per SM
+#if defined(SMT_ABL_OCC16)
+#define SMT_SEQ_AHEAD 1
+#endif
 namespace {
 
+#if defined(SMT_ABL_OCC16)
+constexpr int SEQ_R = 32;
+constexpr int SEQ_RING_SLOTS = 48;
+#else
+constexpr int SEQ_RING_SLOTS = 96;
+#endif
+#if !defined(SMT_ABL_OCC16)
 constexpr int SEQ_R = 96;     // ring entries: three 32-position chunks (span needed: 70 + SEQ_G)
+#endif
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
 constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
 // Measured on B200 at 1080p x 256 (ms per pass; 1.30 as shipped), see DESIGN.md 7:
@@ -32,7 +48,10 @@ constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
 //   compile-time position step for horizontal passes (-27 % instructions in those passes): 1.29;
 //   arm words / support counts fetched two chunks ahead instead of one (6 % of the stall samples sit on their first use): 1.31.
 #ifndef SMT_SEQ_AHEAD
-#define SMT_SEQ_AHEAD 2
+#define SMT_SEQ_AHEAD 1
+#endif
+#ifndef SMT_SEQ_L2PF
+#define SMT_SEQ_L2PF 2  // chunks between the register loads and the L2 prefetch running ahead of them (0 = no prefetch)
 #endif
 constexpr int SEQ_AHEAD = SMT_SEQ_AHEAD;  // chunks of input in flight per warp (register buffers = SEQ_AHEAD + 1)
 constexpr int SEQ_G = 8;      // outputs are emitted in groups of SEQ_G (ring span needed: 70 + SEQ_G <= SEQ_R)
@@ -92,28 +111,21 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                                           const float* __restrict__ src_next, float* __restrict__ dst_first, long long step_rt,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
-                                          float2* __restrict__ wta_first, long long wta_step, int d) {
+                                          float2* __restrict__ wta_first, long long wta_step, int d, int zero) {
     const long long step = CSTEP ? (long long)CSTEP : step_rt;
-    // ---- loads of chunk tb + SEQ_AHEAD*32 (consumed SEQ_AHEAD chunks later: with 8 warps per SM one chunk of loads in flight per
-    // warp does not cover the DRAM latency -- ncu showed 35 % of all stall samples on the first use of a chunk)
-    {
-        const float* p = src_next;
-#pragma unroll
-        for (int k = 0; k < SEQ_CH; ++k) {
-            if (EDGE)
-                vload[k] = (tb + SEQ_AHEAD * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
-            else
-                vload[k] = __ldcs(p);
-            p += step;
-        }
-    }
-    // ---- descriptors of the outputs of this chunk (position tb - 35 + lane) from the arm word / count fetched one
-    // chunk ago; fetch the next chunk's now so that load is never on the critical path
+    // ORDER MATTERS.  ptxas puts every global load of this kernel on ONE scoreboard (SB5 in the SASS), and a scoreboard is a
+    // counter: the first instruction that needs ANY loaded value waits until ALL loads issued before it have landed.
+    // Issuing this chunk's loads at the top (as a prefetch) therefore made the first prefix step wait for them: a full
+    // DRAM round trip per chunk, no overlap at all (28 % long-scoreboard stalls; removing the loads took a pass from
+    // 1.30 to 0.82 ms).  So: (1) consume what the previous chunk fetched -- arm word, support count, vuse[0] -- while the only
+    // loads in flight are a whole chunk old, (2) only then issue this chunk's loads, with an address that depends on the
+    // result of (1) so that the scheduler cannot hoist them, (3) do the rest of the chunk, which needs no loaded value
+    // that has not been waited for already.
+    // ---- (1a) descriptors of the outputs of this chunk (position tb - 35 + lane) from the arm word / count fetched one chunk ago
     {
         const int j = tb - SEQ_LOOK + lane;
         Desc ds{0u, 0u, 1.f, 1.f};
         if ((SEQ_CH == 32 || lane < SEQ_CH) && (!EDGE || (j >= 0 && j < len))) {
-            // unpack here, a whole chunk after the load was issued (unpacking next to the load stalls on it)
             const unsigned aw = horiz ? (pre.armw & 0xffffu) : (pre.armw >> 16);
             const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
             // arms stop at the image border, so the clamps only act on the halo rows of a row band (bandsplit), whose
@@ -126,14 +138,6 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                 ds.rcp = __frcp_rn(ds.cnt);
             }
         }
-        const int jn = j + SEQ_CH;
-        pre.armw = 0u;
-        pre.cnt = 1;
-        if ((SEQ_CH == 32 || lane < SEQ_CH) && jn >= 0 && jn < len) {
-            const long long pix = pbase + pstride * jn;
-            pre.armw = __ldg(reinterpret_cast<const unsigned*>(arms) + pix);  // raw {left,right,top,bottom} bytes
-            if (HAS_SUP) pre.cnt = (int)__ldg(sup + pix);
-        }
         __syncwarp();  // the previous chunk's descriptor reads are done
         if (SEQ_CH == 32 || lane < SEQ_CH) desc[lane] = ds;
         __syncwarp();
@@ -141,10 +145,48 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
     unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;  // slot of E[tb]
     float* dp = dst_first;                                             // output position tb - 35
     float2* wp = wta_first;
+    // ---- (1b) first prefix step
+    *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);  // E[tb]
+    acc = pre_add<NONNEG>(acc, vuse[0]);
+    // ---- (2) loads of chunk tb + SEQ_AHEAD*32 and of the next chunk's arm words; `zero` is 0 at run time
+    const int dep = __float_as_int(acc.a) & zero;
+    {
+        const float* p = src_next + dep;
+#pragma unroll
+        for (int k = 0; k < SEQ_CH; ++k) {
+            if (EDGE)
+                vload[k] = (tb + SEQ_AHEAD * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+            else
+#if defined(SMT_ABL_NOLOAD)
+                vload[k] = __int_as_float(horiz + 0x3f000000);
+#else
+                vload[k] = __ldcs(p);
+#endif
+            p += step;
+        }
+#if SMT_SEQ_L2PF > 0
+        {   // DRAM -> L2 runs further ahead than the scoreboard allows registers to: ONE prefetch instruction per chunk, lane l
+            // asks for the 128-byte row of position tb + (AHEAD + L2PF)*32 + l.  The register loads above then hit L2.
+            const int q = tb + (SEQ_AHEAD + SMT_SEQ_L2PF) * SEQ_CH + lane;
+            if (q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
+        }
+#endif
+        const int jn = tb - SEQ_LOOK + lane + SEQ_CH;
+        pre.armw = 0u;
+        pre.cnt = 1;
+        if ((SEQ_CH == 32 || lane < SEQ_CH) && jn >= 0 && jn < len) {
+            const long long pix = pbase + pstride * jn + dep;
+            pre.armw = __ldg(reinterpret_cast<const unsigned*>(arms) + pix);  // raw {left,right,top,bottom} bytes
+            if (HAS_SUP) pre.cnt = (int)__ldg(sup + pix);
+        }
+    }
+    // ---- (3) the other prefix steps and the outputs
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
-        *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E[tb+k]
-        acc = pre_add<NONNEG>(acc, vuse[k]);
+        if (k > 0) {
+            *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E[tb+k]
+            acc = pre_add<NONNEG>(acc, vuse[k]);
+        }
         if ((k & (SEQ_G - 1)) == SEQ_G - 1) {
 #pragma unroll
             for (int u = 0; u < SEQ_G; ++u) {
@@ -161,6 +203,9 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                         const unsigned who = __ballot_sync(0xffffffffu, key == g);
                         if (lane == 0) *wp = make_float2(key2f_(g), (float)(d + __ffs(who) - 1));  // d = this warp's first disparity
                     } else if (!EDGE || act) {
+#if defined(SMT_ABL_NOSTORE)
+                        if (r == 123456.f)
+#endif
                         __stcs(dp, r);
                     }
                 }
@@ -172,12 +217,12 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 }
 
 constexpr int SEQ_WARPS = 8;  // the 8 warps of a block walk the d-chunks of the same line(s): 1 KB contiguous per pixel
-constexpr int SEQ_SMEM_PER_WARP = SEQ_R * 256 + SEQ_CH * (int)sizeof(Desc);
+constexpr int SEQ_SMEM_PER_WARP = SEQ_RING_SLOTS * 256 + SEQ_CH * (int)sizeof(Desc);
 
 template <bool NONNEG, bool HAS_SUP, bool WTA, int CSTEP = 0>
 __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
-                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial) {
+                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
@@ -200,7 +245,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
     unsigned char* ring_col = s_ring + lane * 8;
 
     pair2 acc{NONNEG ? bias : 0.f, 0.f};
-    // three register buffers rotate: while chunk o is consumed, chunks o+1 and o+2 are in flight (8 KB per warp)
+    // SEQ_AHEAD + 1 register buffers rotate: while chunk o is consumed, the next SEQ_AHEAD chunks are in flight
     float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_AHEAD == 2 ? SEQ_CH : 1];
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
@@ -222,11 +267,11 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
         if (full && tb - SEQ_LOOK >= 0 && tb + (SEQ_AHEAD + 1) * SEQ_CH <= len)                                               \
             seq_chunk<NONNEG, HAS_SUP, false, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,       \
                                                    pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,               \
-                                                   wta_step, chunk * 32);                                                     \
+                                                   wta_step, chunk * 32, zero);                                               \
         else                                                                                                                  \
             seq_chunk<NONNEG, HAS_SUP, true, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,        \
                                                   pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,                \
-                                                  wta_step, chunk * 32);                                                      \
+                                                  wta_step, chunk * 32, zero);                                                \
         ++o;                                                                                                                  \
     }
     for (int o = 0; o < nouter;) {
@@ -417,6 +462,174 @@ static smt_status_t launch_seq2(smt_ctx* ctx, const float* in, float* out, const
     return SMT_OK;
 }
 
+// ================================================================================================ fused pair, half-warp roles
+// The same two passes (A divides, B does not) in one walk at the occupancy of a single pass: a warp covers 16 disparities;
+// lanes 0-15 run pass A on them, lanes 16-31 run pass B on the same 16, every lane owns ONE ring column.  All lanes execute
+// one instruction stream -- ring store, prefix step, descriptor read, two ring reads, difference, division (B divides by
+// 1, which is exact) -- and differ only in where the prefix input comes from (A: the volume; B: its partner's outputs of
+// the previous group of 8, handed over by shuffle) and in who touches memory (A lanes load, B lanes store; 64-byte rows).
+// With chunk base tb and step kk: A stores E_A[tb+kk] and emits j = tb+kk-35; B consumes A-output tb+kk-43, stores
+// E_B[tb+kk-43] in the slot of the same index (so E_B[q] lives at slot (q+43) mod 96) and emits i = tb+kk-78.
+constexpr int SEQH_LAG = SEQ_LOOK + SEQ_G;        // 43: B's prefix position trails A's by this much
+constexpr int SEQH_LOOKB = SEQH_LAG + SEQ_LOOK;   // 78: B's output position trails A's prefix position by this much
+struct PrefetchedH {
+    unsigned armw_a, armw_b;
+    int cnt_a;
+};
+
+template <bool NONNEG, bool EDGE>
+__device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (&rin)[SEQ_G], float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH],
+                                           int tb, int len, bool act, bool isb, const float* __restrict__ src_next,
+                                           float* __restrict__ dst_first, long long step, long long pbase, long long pstride, int horiz,
+                                           const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_col,
+                                           Desc* desc, int lane) {
+    {
+        const float* p = src_next;
+#pragma unroll
+        for (int k = 0; k < SEQ_CH; ++k) {
+            if (EDGE)
+                vload[k] = (!isb && tb + 2 * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+            else
+                vload[k] = !isb ? __ldcs(p) : 0.f;
+            p += step;
+        }
+    }
+    {
+        const int ja = tb - SEQ_LOOK + lane, ib = tb - SEQH_LOOKB + lane;
+        Desc da{0u, 0u, 1.f, 1.f}, db{0u, 0u, 1.f, 1.f};
+        if (!EDGE || (ja >= 0 && ja < len)) {
+            const unsigned aw = horiz ? (pre.armw_a & 0xffffu) : (pre.armw_a >> 16);
+            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
+            da.offa = (unsigned)(max(ja - lo, 0) % SEQ_R) * 256u;
+            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQ_R) * 256u;
+            da.cnt = (float)pre.cnt_a;
+            da.rcp = __frcp_rn(da.cnt);
+        }
+        if (!EDGE || (ib >= 0 && ib < len)) {
+            const unsigned aw = horiz ? (pre.armw_b & 0xffffu) : (pre.armw_b >> 16);
+            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
+            db.offa = (unsigned)((max(ib - lo, 0) + SEQH_LAG) % SEQ_R) * 256u;
+            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQH_LAG) % SEQ_R) * 256u;
+        }
+        const int jn = ja + SEQ_CH, in_ = ib + SEQ_CH;
+        pre.armw_a = pre.armw_b = 0u;
+        pre.cnt_a = 1;
+        if (jn >= 0 && jn < len) {
+            const long long pix = pbase + pstride * jn;
+            pre.armw_a = __ldg(arms + pix);
+            pre.cnt_a = (int)__ldg(sup_a + pix);
+        }
+        if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_);
+        __syncwarp();
+        desc[2 * lane] = da;  // interleaved so that the two halves of the warp read different banks
+        desc[2 * lane + 1] = db;
+        __syncwarp();
+    }
+    unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;
+    const Desc* dsel = desc + (isb ? 1 : 0);
+    float* dp = dst_first;  // B output position tb - 78 (only B lanes store)
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) {
+        *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E_A[tb+k] / E_B[tb+k-43]
+        acc = pre_add<NONNEG>(acc, isb ? rin[k & (SEQ_G - 1)] : vuse[k]);
+        if ((k & (SEQ_G - 1)) == SEQ_G - 1) {
+#pragma unroll
+            for (int u = 0; u < SEQ_G; ++u) {
+                const int kk = k - (SEQ_G - 1) + u;
+                const Desc ds = dsel[2 * kk];
+                const float2 ea = *reinterpret_cast<const float2*>(ring_col + ds.offa);
+                const float2 eb = *reinterpret_cast<const float2*>(ring_col + ds.offb);
+                float r = div_by_count(__fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y)), ds.cnt, ds.rcp);
+                if (EDGE) {
+                    const int ja = tb - SEQ_LOOK + kk, ib = tb - SEQH_LOOKB + kk;
+                    if (isb) {
+                        if (ib >= 0 && ib < len && act) __stcs(dp, r);
+                    } else if (ja < 0 || ja >= len) {
+                        r = 0.f;  // positions outside the line feed zeros into pass B's prefix
+                    }
+                } else if (isb) {
+                    __stcs(dp, r);
+                }
+                dp += step;
+                rin[u] = __shfl_sync(0xffffffffu, r, lane & 15);  // B lanes receive their partner's A output
+            }
+        }
+    }
+}
+
+template <bool NONNEG>
+__global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seqh_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                 const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a, int H,
+                                                                 int W, int D, int horiz, float bias_a, float bias_b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* s_ring = smem_raw + (size_t)warp * (SEQ_R * 256 + 2 * SEQ_CH * (int)sizeof(Desc));
+    Desc* s_desc = reinterpret_cast<Desc*>(s_ring + SEQ_R * 256);
+    const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
+    const int nh = (D + 15) >> 4;  // 16-disparity groups per line
+    const long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
+    const int line = (int)(wg / nh), hc = (int)(wg - (long long)line * nh);
+    const int len = horiz ? W : H;
+    if (line >= (horiz ? H : W)) return;
+    const bool isb = lane >= 16;
+    const int d = hc * 16 + (lane & 15);
+    const bool act = d < D;
+    const bool full = hc * 16 + 16 <= D;
+    const long long pstride = horiz ? 1 : (long long)W;
+    const long long pbase = horiz ? (long long)line * W : (long long)line;
+    const long long step = pstride * D;
+    const float* src = in + pbase * D + (act ? d : 0);
+    float* dst = out + pbase * D + (act ? d : 0);
+    unsigned char* ring_col = s_ring + lane * 8;
+
+    pair2 acc{NONNEG ? (isb ? bias_b : bias_a) : 0.f, 0.f};
+    float rin[SEQ_G];
+#pragma unroll
+    for (int u = 0; u < SEQ_G; ++u) rin[u] = 0.f;
+    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) {
+        va[k] = (!isb && k < len && act) ? __ldcs(src + step * k) : 0.f;
+        vb[k] = (!isb && SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
+    }
+    PrefetchedH pre{0u, 0u, 1};
+    const int nouter = (len + SEQH_LOOKB + SEQ_CH - 1) / SEQ_CH;
+#define SMT_SEQH_STEP(USE, LOAD)                                                                                              \
+    if (o < nouter) {                                                                                                         \
+        const int tb = o * SEQ_CH;                                                                                            \
+        const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                               \
+        float* dst_first = dst + step * (tb - SEQH_LOOKB);                                                                    \
+        if (full && tb - SEQH_LOOKB >= 0 && tb + 3 * SEQ_CH <= len)                                                           \
+            seqh_chunk<NONNEG, false>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride, \
+                                      horiz, arms, sup_a, ring_col, s_desc, lane);                                            \
+        else                                                                                                                  \
+            seqh_chunk<NONNEG, true>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride,  \
+                                     horiz, arms, sup_a, ring_col, s_desc, lane);                                             \
+        ++o;                                                                                                                  \
+    }
+    for (int o = 0; o < nouter;) {
+        SMT_SEQH_STEP(va, vc)
+        SMT_SEQH_STEP(vb, va)
+        SMT_SEQH_STEP(vc, vb)
+    }
+#undef SMT_SEQH_STEP
+}
+
+template <bool NONNEG>
+static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
+                                int horiz, float bias_a, float bias_b) {
+    constexpr size_t smem = (size_t)SEQ_WARPS * (SEQ_R * 256 + 2 * SEQ_CH * sizeof(Desc));
+    static bool attr_set = false;
+    if (!attr_set) {
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqh_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long nwarps = (long long)(horiz ? H : W) * ((D + 15) / 16);
+    SMT_LAUNCH(ctx, (agg_seqh_kernel<NONNEG>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
+               bias_b);
+    return SMT_OK;
+}
+
 template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
                                int horiz, float bias, float2* wta_partial = nullptr) {
@@ -436,11 +649,11 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
             attr2 = true;
         }
         SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
-                   horiz, bias, wta_partial);
+                   horiz, bias, wta_partial, 0);
         return SMT_OK;
     }
     SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
-               bias, wta_partial);
+               bias, wta_partial, 0);
     return SMT_OK;
 }
 
@@ -484,6 +697,10 @@ smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* ar
 smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
                             int horiz, bool nonneg, float bias_a, float bias_b) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    static const bool two_rings = getenv("SMT_AGG_FUSE") != nullptr && std::string(getenv("SMT_AGG_FUSE")) == "rings";
+    if (!two_rings)
+        return nonneg ? launch_seqh<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
+                      : launch_seqh<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
     return nonneg ? launch_seq2<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
                   : launch_seq2<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
 }
