@@ -54,6 +54,17 @@ constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
 #define SMT_SEQ_L2PF 2  // chunks between the register loads and the L2 prefetch running ahead of them (0 = no prefetch)
 #endif
 constexpr int SEQ_AHEAD = SMT_SEQ_AHEAD;  // chunks of input in flight per warp (register buffers = SEQ_AHEAD + 1)
+#ifndef SMT_SEQ_PIPE
+#define SMT_SEQ_PIPE 1
+#endif
+#ifndef SMT_SEQ_DLAG
+#define SMT_SEQ_DLAG 4
+#endif
+#ifndef SMT_SEQ_RLAG
+#define SMT_SEQ_RLAG 4
+#endif
+constexpr int SEQ_DLAG = SMT_SEQ_DLAG;   // descriptor read this many positions ahead of its ring reads
+constexpr int SEQ_RLAG = SMT_SEQ_RLAG;   // ring reads consumed this many positions after they are issued
 constexpr int SEQ_G = 8;      // outputs are emitted in groups of SEQ_G (ring span needed: 70 + SEQ_G <= SEQ_R)
 
 struct pair2 {
@@ -180,7 +191,52 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
             if (HAS_SUP) pre.cnt = (int)__ldg(sup + pix);
         }
     }
-    // ---- (3) the other prefix steps and the outputs
+    // ---- (3) the other prefix steps and the outputs, software-pipelined over the 32 positions (everything is unrolled, the
+    // arrays are registers): the descriptor of output k is read SEQ_DLAG steps before its two ring reads, which are issued
+    // right after the prefix step that completes them (E[tb+k] is the newest entry output k can need) and consumed
+    // SEQ_RLAG steps later.  Left alone the compiler serialises descriptor read -> ring reads -> arithmetic per output and
+    // every output pays two shared-memory round trips (ncu: 32 % short-scoreboard stalls).
+#if SMT_SEQ_PIPE
+    {
+        Desc dsc[SEQ_CH];
+        float2 ea[SEQ_CH], eb[SEQ_CH];
+#pragma unroll
+        for (int u = 0; u < SEQ_DLAG; ++u) dsc[u] = desc[u];  // broadcast reads
+#pragma unroll
+        for (int k = 0; k < SEQ_CH + SEQ_RLAG; ++k) {
+            if (k < SEQ_CH) {
+                if (k > 0) {
+                    *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E[tb+k]
+                    acc = pre_add<NONNEG>(acc, vuse[k]);
+                }
+                ea[k] = *reinterpret_cast<const float2*>(ring_col + dsc[k].offa);
+                eb[k] = *reinterpret_cast<const float2*>(ring_col + dsc[k].offb);
+                if (k + SEQ_DLAG < SEQ_CH) dsc[k + SEQ_DLAG] = desc[k + SEQ_DLAG];
+            }
+            if (k >= SEQ_RLAG) {
+                const int kk = k - SEQ_RLAG;
+                const bool inside = !EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len);  // warp-uniform
+                float r = __fadd_rn(__fsub_rn(eb[kk].x, ea[kk].x), __fsub_rn(eb[kk].y, ea[kk].y));
+                if (HAS_SUP) r = div_by_count(r, dsc[kk].cnt, dsc[kk].rcp);
+                if (WTA) {
+                    if (inside) {
+                        const unsigned key = act ? f2key_(r) : 0xffffffffu;
+                        const unsigned g = __reduce_min_sync(0xffffffffu, key);
+                        const unsigned who = __ballot_sync(0xffffffffu, key == g);
+                        if (lane == 0) *wp = make_float2(key2f_(g), (float)(d + __ffs(who) - 1));  // d = this warp's first disparity
+                    }
+                } else if (inside && (!EDGE || act)) {
+#if defined(SMT_ABL_NOSTORE)
+                    if (r == 123456.f)
+#endif
+                    __stcs(dp, r);
+                }
+                dp += step;
+                wp += wta_step;
+            }
+        }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
         if (k > 0) {
@@ -214,6 +270,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
             }
         }
     }
+#endif
 }
 
 constexpr int SEQ_WARPS = 8;  // the 8 warps of a block walk the d-chunks of the same line(s): 1 KB contiguous per pixel
@@ -482,18 +539,8 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
                                            int tb, int len, bool act, bool isb, const float* __restrict__ src_next,
                                            float* __restrict__ dst_first, long long step, long long pbase, long long pstride, int horiz,
                                            const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_col,
-                                           Desc* desc, int lane) {
-    {
-        const float* p = src_next;
-#pragma unroll
-        for (int k = 0; k < SEQ_CH; ++k) {
-            if (EDGE)
-                vload[k] = (!isb && tb + 2 * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
-            else
-                vload[k] = !isb ? __ldcs(p) : 0.f;
-            p += step;
-        }
-    }
+                                           Desc* desc, int lane, int zero) {
+    // same order as seq_chunk: consume what the previous chunk fetched, then issue this chunk's loads, then the rest
     {
         const int ja = tb - SEQ_LOOK + lane, ib = tb - SEQH_LOOKB + lane;
         Desc da{0u, 0u, 1.f, 1.f}, db{0u, 0u, 1.f, 1.f};
@@ -511,15 +558,6 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
             db.offa = (unsigned)((max(ib - lo, 0) + SEQH_LAG) % SEQ_R) * 256u;
             db.offb = (unsigned)((min(ib + hi + 1, len) + SEQH_LAG) % SEQ_R) * 256u;
         }
-        const int jn = ja + SEQ_CH, in_ = ib + SEQ_CH;
-        pre.armw_a = pre.armw_b = 0u;
-        pre.cnt_a = 1;
-        if (jn >= 0 && jn < len) {
-            const long long pix = pbase + pstride * jn;
-            pre.armw_a = __ldg(arms + pix);
-            pre.cnt_a = (int)__ldg(sup_a + pix);
-        }
-        if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_);
         __syncwarp();
         desc[2 * lane] = da;  // interleaved so that the two halves of the warp read different banks
         desc[2 * lane + 1] = db;
@@ -528,10 +566,41 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
     unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;
     const Desc* dsel = desc + (isb ? 1 : 0);
     float* dp = dst_first;  // B output position tb - 78 (only B lanes store)
+    *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);
+    acc = pre_add<NONNEG>(acc, isb ? rin[0] : vuse[0]);
+    const int dep = __float_as_int(acc.a) & zero;
+    {
+        const float* p = src_next + dep;
+#pragma unroll
+        for (int k = 0; k < SEQ_CH; ++k) {
+            if (EDGE)
+                vload[k] = (!isb && tb + SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+            else
+                vload[k] = !isb ? __ldcs(p) : 0.f;
+            p += step;
+        }
+#if SMT_SEQ_L2PF > 0
+        {
+            const int q = tb + (1 + SMT_SEQ_L2PF) * SEQ_CH + lane;
+            if (q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
+        }
+#endif
+        const int jn = tb - SEQ_LOOK + lane + SEQ_CH, in_ = tb - SEQH_LOOKB + lane + SEQ_CH;
+        pre.armw_a = pre.armw_b = 0u;
+        pre.cnt_a = 1;
+        if (jn >= 0 && jn < len) {
+            const long long pix = pbase + pstride * jn + dep;
+            pre.armw_a = __ldg(arms + pix);
+            pre.cnt_a = (int)__ldg(sup_a + pix);
+        }
+        if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_ + dep);
+    }
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
-        *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E_A[tb+k] / E_B[tb+k-43]
-        acc = pre_add<NONNEG>(acc, isb ? rin[k & (SEQ_G - 1)] : vuse[k]);
+        if (k > 0) {
+            *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E_A[tb+k] / E_B[tb+k-43]
+            acc = pre_add<NONNEG>(acc, isb ? rin[k & (SEQ_G - 1)] : vuse[k]);
+        }
         if ((k & (SEQ_G - 1)) == SEQ_G - 1) {
 #pragma unroll
             for (int u = 0; u < SEQ_G; ++u) {
@@ -560,7 +629,7 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
 template <bool NONNEG>
 __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seqh_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                  const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a, int H,
-                                                                 int W, int D, int horiz, float bias_a, float bias_b) {
+                                                                 int W, int D, int horiz, float bias_a, float bias_b, int zero) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * (SEQ_R * 256 + 2 * SEQ_CH * (int)sizeof(Desc));
@@ -586,31 +655,27 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seqh_kernel(const float* _
     float rin[SEQ_G];
 #pragma unroll
     for (int u = 0; u < SEQ_G; ++u) rin[u] = 0.f;
-    float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_CH];
+    float va[SEQ_CH], vb[SEQ_CH];
 #pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) {
-        va[k] = (!isb && k < len && act) ? __ldcs(src + step * k) : 0.f;
-        vb[k] = (!isb && SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
-    }
+    for (int k = 0; k < SEQ_CH; ++k) va[k] = (!isb && k < len && act) ? __ldcs(src + step * k) : 0.f;
     PrefetchedH pre{0u, 0u, 1};
     const int nouter = (len + SEQH_LOOKB + SEQ_CH - 1) / SEQ_CH;
 #define SMT_SEQH_STEP(USE, LOAD)                                                                                              \
     if (o < nouter) {                                                                                                         \
         const int tb = o * SEQ_CH;                                                                                            \
-        const float* src_next = src + step * (tb + 2 * SEQ_CH);                                                               \
+        const float* src_next = src + step * (tb + SEQ_CH);                                                                   \
         float* dst_first = dst + step * (tb - SEQH_LOOKB);                                                                    \
-        if (full && tb - SEQH_LOOKB >= 0 && tb + 3 * SEQ_CH <= len)                                                           \
+        if (full && tb - SEQH_LOOKB >= 0 && tb + 2 * SEQ_CH <= len)                                                           \
             seqh_chunk<NONNEG, false>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride, \
-                                      horiz, arms, sup_a, ring_col, s_desc, lane);                                            \
+                                      horiz, arms, sup_a, ring_col, s_desc, lane, zero);                                      \
         else                                                                                                                  \
             seqh_chunk<NONNEG, true>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride,  \
-                                     horiz, arms, sup_a, ring_col, s_desc, lane);                                             \
+                                     horiz, arms, sup_a, ring_col, s_desc, lane, zero);                                       \
         ++o;                                                                                                                  \
     }
     for (int o = 0; o < nouter;) {
-        SMT_SEQH_STEP(va, vc)
+        SMT_SEQH_STEP(va, vb)
         SMT_SEQH_STEP(vb, va)
-        SMT_SEQH_STEP(vc, vb)
     }
 #undef SMT_SEQH_STEP
 }
@@ -626,7 +691,7 @@ static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const
     }
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 15) / 16);
     SMT_LAUNCH(ctx, (agg_seqh_kernel<NONNEG>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
-               bias_b);
+               bias_b, 0);
     return SMT_OK;
 }
 
