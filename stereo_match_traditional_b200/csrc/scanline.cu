@@ -68,7 +68,10 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&r
 template <int DPL, int VW, int PF, bool VERT>
 __global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__ cost, const float* __restrict__ gray, int H, int W,
                                                        int D, float p1, float p2init, int dir, float* __restrict__ path_out,
-                                                       const float* acc_in, float* acc_out, float* __restrict__ disp) {
+                                                       const float* acc_in, float* acc_out, float* __restrict__ disp, int zero) {
+    __shared__ float s_p2[256];  // max(p1, p2Init / (d + 1)) for integer grey differences d
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_p2[i] = fmaxf(p1, __fdiv_rn(p2init, __fadd_rn((float)i, 1.f)));
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nlines = VERT ? W : H;
@@ -104,80 +107,122 @@ __global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__
     const float gstart = __ldg(gray + pix0);
     float glast = gstart;
 
+    // ptxas tracks every global load of this kernel on one scoreboard, and a scoreboard is a counter: the first use of ANY
+    // loaded value waits for ALL loads issued before it.  So the ring is consumed and refilled in groups of G = PF/2
+    // steps: (1) copy the group's rows out of the ring (the one wait, for loads that are at least a group old), (2) refill
+    // those slots with the steps PF ahead -- the address depends on a value read in (1), so the loads cannot be hoisted
+    // above the wait -- and ask L2 for the rows further ahead, (3) run the group's recurrence steps, which touch no
+    // in-flight register.
+    constexpr int G = PF / 2 > 0 ? PF / 2 : 1;
+#ifndef SMT_SCAN_L2AHEAD
+#define SMT_SCAN_L2AHEAD 0
+#endif
+    constexpr int L2AHEAD = SMT_SCAN_L2AHEAD;  // steps between the register refill and the L2 prefetch running ahead of it (0: none)
     for (int s0 = 0; s0 < N; s0 += PF) {
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int s = s0 + u;
-            if (s < N) {
-                const long long pix = pix0 + pstep * s;
-                float cur[DPL];
-                if (s == 0) {
-                    // first pixel of the path: L = C (:153,:215)
+        for (int g0 = 0; g0 < PF; g0 += G) {
+            float cC[G][DPL], cA[G][DPL], cG[G];
 #pragma unroll
-                    for (int k = 0; k < DPL; ++k) cur[k] = (k < nvalid) ? ringC[u][k] : PAD;
-                } else {
-                    const float g = ringG[u];
-                    const float gref = VERT ? gstart : glast;
-                    // p2 = max(p1, p2Init / (|g - g_ref| + 1))  (:171,:232)
-                    const float p2 = fmaxf(p1, __fdiv_rn(p2init, __fadd_rn(fabsf(__fsub_rn(g, gref)), 1.f)));
-                    const float l4 = __fadd_rn(m, p2);
-                    float up_nb = __shfl_up_sync(0xffffffffu, prev[DPL - 1], 1);   // prev[d-1] of my first element
-                    float dn_nb = __shfl_down_sync(0xffffffffu, prev[0], 1);       // prev[d+1] of my last element
-                    if (lane == 0) up_nb = PAD;
-                    if (lane == 31) dn_nb = PAD;
+            for (int v = 0; v < G; ++v) {
+                cG[v] = ringG[g0 + v];
 #pragma unroll
-                    for (int k = 0; k < DPL; ++k) {
-                        const float l1 = prev[k];
-                        const float lm = (k == 0) ? up_nb : prev[k - 1];
-                        const float lp = (k == DPL - 1) ? dn_nb : prev[k + 1];
-                        const float l2 = VERT ? __fadd_rn(l1, p1) : __fadd_rn(lm, p1);  // (:238) vs (:177)
-                        const float l3 = __fadd_rn(lp, p1);
-                        const float mn = fminf(fminf(l1, l2), fminf(l3, l4));
-                        const float v = __fsub_rn(__fadd_rn(ringC[u][k], mn), m);
-                        cur[k] = (k < nvalid) ? v : PAD;
-                    }
-                    glast = g;
+                for (int k = 0; k < DPL; ++k) {
+                    cC[v][k] = ringC[g0 + v][k];
+                    cA[v][k] = has_acc ? ringA[g0 + v][k] : 0.f;
                 }
-                // minimum over d of the new row (capped by the 0xffff pads, :162-166,:169,:182)
-                float lm_ = PAD;
+            }
+            const int dep = (__float_as_int(cC[0][0]) & zero) + (has_acc ? (__float_as_int(cA[0][0]) & zero) : 0) +
+                            (__float_as_int(cG[0]) & zero);
 #pragma unroll
-                for (int k = 0; k < DPL; ++k) lm_ = fminf(lm_, cur[k]);
-                m = key2f(__reduce_min_sync(0xffffffffu, f2key(lm_)));
+            for (int v = 0; v < G; ++v) {
+                const int sn = s0 + g0 + v + PF;
+                if (sn < N) {
+                    const long long pixn = pix0 + pstep * sn + dep;
+                    load_row<DPL, VW>(cost + pixn * D + d0, ringC[g0 + v], nvalid);
+                    if (has_acc) load_row<DPL, VW>(acc_in + pixn * D + d0, ringA[g0 + v], nvalid);
+                    ringG[g0 + v] = __ldg(gray + pix0 + gstep * sn + dep);
+                }
+                const int sp = sn + L2AHEAD;
+                if (L2AHEAD > 0 && sp < N && nvalid > 0) {
+                    const long long pixp = pix0 + pstep * sp + dep;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(cost + pixp * D + d0));
+                    if (has_acc) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc_in + pixp * D + d0));
+                }
+            }
 #pragma unroll
-                for (int k = 0; k < DPL; ++k) prev[k] = cur[k];
-
-                if (path_out) store_row<DPL, VW>(path_out + pix * D + d0, cur, nvalid);
-                if (has_acc || acc_out || disp) {
-                    float a[DPL];
+            for (int v = 0; v < G; ++v) {
+                const int s = s0 + g0 + v;
+                if (s < N) {
+                    const long long pix = pix0 + pstep * s;
+                    float cur[DPL];
+                    if (s == 0) {
+                        // first pixel of the path: L = C (:153,:215)
 #pragma unroll
-                    for (int k = 0; k < DPL; ++k) a[k] = has_acc ? __fadd_rn(ringA[u][k], cur[k]) : cur[k];
-                    if (acc_out) store_row<DPL, VW>(acc_out + pix * D + d0, a, nvalid);
-                    if (disp) {
-                        // first minimum over d: ascending k inside the lane, lowest lane among equals (:51-58)
-                        unsigned bk = 0xffffffffu;
-                        int bd = 0;
+                        for (int k = 0; k < DPL; ++k) cur[k] = (k < nvalid) ? cC[v][k] : PAD;
+                    } else {
+                        const float g = cG[v];
+                        const float gref = VERT ? gstart : glast;
+                        // p2 = max(p1, p2Init / (|g - g_ref| + 1))  (:171,:232).  Grey differences are integers 0..255 for every
+                        // image the drivers produce: those quotients come from a table (the IEEE division is a subroutine call,
+                        // and a call waits for every load in flight); anything else takes the division itself.
+                        const float ad = fabsf(__fsub_rn(g, gref));
+                        const int ai = (int)ad;
+                        float p2;
+                        if ((float)ai == ad && ai < 256)
+                            p2 = s_p2[ai];
+                        else
+                            p2 = fmaxf(p1, __fdiv_rn(p2init, __fadd_rn(ad, 1.f)));
+                        const float l4 = __fadd_rn(m, p2);
+                        float up_nb = __shfl_up_sync(0xffffffffu, prev[DPL - 1], 1);   // prev[d-1] of my first element
+                        float dn_nb = __shfl_down_sync(0xffffffffu, prev[0], 1);       // prev[d+1] of my last element
+                        if (lane == 0) up_nb = PAD;
+                        if (lane == 31) dn_nb = PAD;
 #pragma unroll
                         for (int k = 0; k < DPL; ++k) {
-                            const unsigned key = f2key(a[k]);
-                            if (k < nvalid && key < bk) {
-                                bk = key;
-                                bd = d0 + k;
-                            }
+                            const float l1 = prev[k];
+                            const float lm = (k == 0) ? up_nb : prev[k - 1];
+                            const float lp = (k == DPL - 1) ? dn_nb : prev[k + 1];
+                            const float l2 = VERT ? __fadd_rn(l1, p1) : __fadd_rn(lm, p1);  // (:238) vs (:177)
+                            const float l3 = __fadd_rn(lp, p1);
+                            const float mn = fminf(fminf(l1, l2), fminf(l3, l4));
+                            const float vv = __fsub_rn(__fadd_rn(cC[v][k], mn), m);
+                            cur[k] = (k < nvalid) ? vv : PAD;
                         }
-                        const unsigned gk = __reduce_min_sync(0xffffffffu, bk);
-                        const unsigned who = __ballot_sync(0xffffffffu, bk == gk && nvalid > 0);
-                        const int src = who ? (__ffs(who) - 1) : 0;
-                        const int best = __shfl_sync(0xffffffffu, bd, src);
-                        if (lane == 0) disp[pix] = (float)best;
+                        glast = g;
                     }
-                }
-                // refill this ring slot with step s+PF
-                const int sn = s + PF;
-                if (sn < N) {
-                    const long long pixn = pix0 + pstep * sn;
-                    load_row<DPL, VW>(cost + pixn * D + d0, ringC[u], nvalid);
-                    if (has_acc) load_row<DPL, VW>(acc_in + pixn * D + d0, ringA[u], nvalid);
-                    ringG[u] = __ldg(gray + pix0 + gstep * sn);
+                    // minimum over d of the new row (capped by the 0xffff pads, :162-166,:169,:182)
+                    float lm_ = PAD;
+#pragma unroll
+                    for (int k = 0; k < DPL; ++k) lm_ = fminf(lm_, cur[k]);
+                    m = key2f(__reduce_min_sync(0xffffffffu, f2key(lm_)));
+#pragma unroll
+                    for (int k = 0; k < DPL; ++k) prev[k] = cur[k];
+
+                    if (path_out) store_row<DPL, VW>(path_out + pix * D + d0, cur, nvalid);
+                    if (has_acc || acc_out || disp) {
+                        float a[DPL];
+#pragma unroll
+                        for (int k = 0; k < DPL; ++k) a[k] = has_acc ? __fadd_rn(cA[v][k], cur[k]) : cur[k];
+                        if (acc_out) store_row<DPL, VW>(acc_out + pix * D + d0, a, nvalid);
+                        if (disp) {
+                            // first minimum over d: ascending k inside the lane, lowest lane among equals (:51-58)
+                            unsigned bk = 0xffffffffu;
+                            int bd = 0;
+#pragma unroll
+                            for (int k = 0; k < DPL; ++k) {
+                                const unsigned key = f2key(a[k]);
+                                if (k < nvalid && key < bk) {
+                                    bk = key;
+                                    bd = d0 + k;
+                                }
+                            }
+                            const unsigned gk = __reduce_min_sync(0xffffffffu, bk);
+                            const unsigned who = __ballot_sync(0xffffffffu, bk == gk && nvalid > 0);
+                            const int src = who ? (__ffs(who) - 1) : 0;
+                            const int best = __shfl_sync(0xffffffffu, bd, src);
+                            if (lane == 0) disp[pix] = (float)best;
+                        }
+                    }
                 }
             }
         }
@@ -191,16 +236,16 @@ static smt_status_t launch_paths(smt_ctx* ctx, const float* cost, const float* g
     // pass 1: left -> L (scratch unless the caller wants the left volume)
     float* Lbuf = left ? left : scratch;
     SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, false>), cdiv(H, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, +1, Lbuf,
-               (const float*)nullptr, (float*)nullptr, (float*)nullptr);
+               (const float*)nullptr, (float*)nullptr, (float*)nullptr, 0);
     // pass 2: right; acc = left + right  (in place over scratch when it holds `left`)
     SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, false>), cdiv(H, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, -1, right,
-               (const float*)Lbuf, scratch, (float*)nullptr);
+               (const float*)Lbuf, scratch, (float*)nullptr, 0);
     // pass 3: up; acc += up
     SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, true>), cdiv(W, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, +1, up,
-               (const float*)scratch, scratch, (float*)nullptr);
+               (const float*)scratch, scratch, (float*)nullptr, 0);
     // pass 4: down; acc += down -> sum (optional) and WTA (optional)
     SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, true>), cdiv(W, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, -1, down,
-               (const float*)scratch, sum, disp);
+               (const float*)scratch, sum, disp, 0);
     return SMT_OK;
 }
 
