@@ -221,8 +221,9 @@ struct Pass {
 
 }  // namespace
 
+smt_status_t k_transpose_maps(smt_ctx* ctx, const uint8_t* arms8, const uint16_t* sup, int H, int W, uint8_t* armsT, uint16_t* supT);
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                            int horiz, bool nonneg, float bias);  // cross_agg_seq.cu
+                            int horiz, bool nonneg, float bias, int tmaps);  // cross_agg_seq.cu
 smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
                             int horiz, bool nonneg, float bias_a, float bias_b);
 smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D, int horiz,
@@ -262,6 +263,11 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
     // default: the streaming one-warp-per-line kernel (cross_agg_seq.cu); SMT_AGG_KERNEL=tile selects the tiled one
     static const bool use_tile = getenv("SMT_AGG_KERNEL") != nullptr && std::string(getenv("SMT_AGG_KERNEL")) == "tile";
     if (!use_tile) {
+        // vertical walks read the arm words and sup0 of 32 consecutive rows at a time: give them [W][H] copies
+        const size_t npix = (size_t)H * W;
+        SMT_ALLOC(ctx, armsT, npix * 4);
+        SMT_ALLOC(ctx, sup0T, npix * sizeof(uint16_t));
+        SMT_TRY(k_transpose_maps(ctx, arms8, sup0, H, W, armsT.as<uint8_t>(), sup0T.as<uint16_t>()));
         for (size_t k = 0; k < passes.size();) {
             // a dividing pass followed by a non-dividing pass in the same direction (V,V / H,H) runs as one fused walk
             const bool pair = fuse_pairs && k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz && passes[k].sup &&
@@ -276,8 +282,11 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
                 SMT_TRY(k_agg_seq_pair(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg, b_sum, b_plain));
                 k += 2;
             } else {
-                SMT_TRY(k_agg_seq_pass(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg,
-                                       passes[k].sup ? b_sum : b_plain));
+                if (passes[k].horiz)
+                    SMT_TRY(k_agg_seq_pass(ctx, cur, oth, arms8, passes[k].sup, H, W, D, 1, nonneg, passes[k].sup ? b_sum : b_plain, 0));
+                else
+                    SMT_TRY(k_agg_seq_pass(ctx, cur, oth, armsT.as<uint8_t>(), passes[k].sup ? sup0T.as<uint16_t>() : nullptr, H, W, D, 0,
+                                           nonneg, passes[k].sup ? b_sum : b_plain, 1));
                 k += 1;
             }
             float* sw = cur;

@@ -124,6 +124,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
                                           float2* __restrict__ wta_first, long long wta_step, int d, int zero) {
     const long long step = CSTEP ? (long long)CSTEP : step_rt;
+    const long long step_b = step * 4;  // byte steps on char pointers: one 64-bit add per address instead of index + shift
     // ORDER MATTERS.  ptxas puts every global load of this kernel on ONE scoreboard (SB5 in the SASS), and a scoreboard is a
     // counter: the first instruction that needs ANY loaded value waits until ALL loads issued before it have landed.
     // Issuing this chunk's loads at the top (as a prefetch) therefore made the first prefix step wait for them: a full
@@ -154,7 +155,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
         __syncwarp();
     }
     unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;  // slot of E[tb]
-    float* dp = dst_first;                                             // output position tb - 35
+    char* dp = reinterpret_cast<char*>(dst_first);                     // output position tb - 35
     float2* wp = wta_first;
     // ---- (1b) first prefix step
     *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);  // E[tb]
@@ -162,18 +163,18 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
     // ---- (2) loads of chunk tb + SEQ_AHEAD*32 and of the next chunk's arm words; `zero` is 0 at run time
     const int dep = __float_as_int(acc.a) & zero;
     {
-        const float* p = src_next + dep;
+        const char* p = reinterpret_cast<const char*>(src_next + dep);
 #pragma unroll
         for (int k = 0; k < SEQ_CH; ++k) {
             if (EDGE)
-                vload[k] = (tb + SEQ_AHEAD * SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+                vload[k] = (tb + SEQ_AHEAD * SEQ_CH + k < len && act) ? __ldcs(reinterpret_cast<const float*>(p)) : 0.f;
             else
 #if defined(SMT_ABL_NOLOAD)
                 vload[k] = __int_as_float(horiz + 0x3f000000);
 #else
-                vload[k] = __ldcs(p);
+                vload[k] = __ldcs(reinterpret_cast<const float*>(p));
 #endif
-            p += step;
+            p += step_b;
         }
 #if SMT_SEQ_L2PF > 0
         {   // DRAM -> L2 runs further ahead than the scoreboard allows registers to: ONE prefetch instruction per chunk, lane l
@@ -229,9 +230,9 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 #if defined(SMT_ABL_NOSTORE)
                     if (r == 123456.f)
 #endif
-                    __stcs(dp, r);
+                    __stcs(reinterpret_cast<float*>(dp), r);
                 }
-                dp += step;
+                dp += step_b;
                 wp += wta_step;
             }
         }
@@ -262,10 +263,10 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 #if defined(SMT_ABL_NOSTORE)
                         if (r == 123456.f)
 #endif
-                        __stcs(dp, r);
+                        __stcs(reinterpret_cast<float*>(dp), r);
                     }
                 }
-                dp += step;
+                dp += step_b;
                 wp += wta_step;
             }
         }
@@ -279,7 +280,7 @@ constexpr int SEQ_SMEM_PER_WARP = SEQ_RING_SLOTS * 256 + SEQ_CH * (int)sizeof(De
 template <bool NONNEG, bool HAS_SUP, bool WTA, int CSTEP = 0>
 __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
-                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero) {
+                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero, int tmaps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
@@ -300,6 +301,10 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
     const float* src = in + pbase * D + (act ? d : 0);
     float* dst = out + pbase * D + (act ? d : 0);
     unsigned char* ring_col = s_ring + lane * 8;
+    // index of position j of this line in the arm / support-count maps: [H][W], or [W][H] copies for vertical walks (tmaps)
+    // so that the 32 lanes of a descriptor fetch read consecutive entries instead of 32 different rows
+    const long long mstride = (!horiz && tmaps) ? 1 : pstride;
+    const long long mbase = (!horiz && tmaps) ? (long long)line * H : pbase;
 
     pair2 acc{NONNEG ? bias : 0.f, 0.f};
     // SEQ_AHEAD + 1 register buffers rotate: while chunk o is consumed, the next SEQ_AHEAD chunks are in flight
@@ -322,12 +327,12 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __
         const long long wta_step = pstride * nchunk;                                                                          \
         /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
         if (full && tb - SEQ_LOOK >= 0 && tb + (SEQ_AHEAD + 1) * SEQ_CH <= len)                                               \
-            seq_chunk<NONNEG, HAS_SUP, false, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,       \
-                                                   pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,               \
+            seq_chunk<NONNEG, HAS_SUP, false, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, mbase,       \
+                                                   mstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,               \
                                                    wta_step, chunk * 32, zero);                                               \
         else                                                                                                                  \
-            seq_chunk<NONNEG, HAS_SUP, true, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase,        \
-                                                  pstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,                \
+            seq_chunk<NONNEG, HAS_SUP, true, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, mbase,        \
+                                                  mstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,                \
                                                   wta_step, chunk * 32, zero);                                                \
         ++o;                                                                                                                  \
     }
@@ -697,7 +702,7 @@ static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const
 
 template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
-                               int horiz, float bias, float2* wta_partial = nullptr) {
+                               int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0) {
     constexpr size_t smem = (size_t)SEQ_WARPS * SEQ_SMEM_PER_WARP;
     static bool attr_set = false;
     if (!attr_set) {
@@ -714,24 +719,54 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
             attr2 = true;
         }
         SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
-                   horiz, bias, wta_partial, 0);
+                   horiz, bias, wta_partial, 0, tmaps);
         return SMT_OK;
     }
     SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
-               bias, wta_partial, 0);
+               bias, wta_partial, 0, tmaps);
     return SMT_OK;
 }
 
 }  // namespace
 
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                            int horiz, bool nonneg, float bias) {
+                            int horiz, bool nonneg, float bias, int tmaps) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     if (nonneg)
-        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
-                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
-    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias)
-               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias);
+        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps)
+                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps);
+    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps)
+               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps);
+}
+
+// [H][W] -> [W][H] copies of the arm words and of one support-count map for the vertical walks
+__global__ void __launch_bounds__(256) transpose_maps_kernel(const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
+                                                             uchar4* __restrict__ armsT, uint16_t* __restrict__ supT) {
+    __shared__ unsigned ta[32][33];
+    __shared__ uint16_t ts[32][34];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int y = y0 + r, x = x0 + tx;
+        if (y < H && x < W) {
+            ta[r][tx] = reinterpret_cast<const unsigned*>(arms)[(size_t)y * W + x];
+            ts[r][tx] = sup ? sup[(size_t)y * W + x] : (uint16_t)0;
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + r, y = y0 + tx;
+        if (y < H && x < W) {
+            reinterpret_cast<unsigned*>(armsT)[(size_t)x * H + y] = ta[tx][r];
+            if (supT) supT[(size_t)x * H + y] = ts[tx][r];
+        }
+    }
+}
+smt_status_t k_transpose_maps(smt_ctx* ctx, const uint8_t* arms8, const uint16_t* sup, int H, int W, uint8_t* armsT, uint16_t* supT) {
+    dim3 grid(cdiv(W, 32), cdiv(H, 32));
+    SMT_LAUNCH(ctx, transpose_maps_kernel, grid, 256, 0, reinterpret_cast<const uchar4*>(arms8), sup, H, W,
+               reinterpret_cast<uchar4*>(armsT), supT);
+    return SMT_OK;
 }
 
 // chunk partials -> first-minimum disparity (ascending chunks, strict '<': AD-Census.h:359-372)
@@ -802,7 +837,7 @@ smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t swee
     const bool nonneg = vmax > 0.f && vmax < 1e30f;
     float b = 1.f;
     while (nonneg && b < vmax) b *= 2.f;
-    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, divides ? b * 128.f : b);
+    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, divides ? b * 128.f : b, 0);
 }
 
 }  // extern "C"
