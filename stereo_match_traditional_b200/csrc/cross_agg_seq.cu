@@ -32,14 +32,19 @@ namespace {
 #if defined(SMT_ABL_OCC16)
 constexpr int SEQ_R = 32;
 constexpr int SEQ_RING_SLOTS = 48;
-#else
+#elif defined(SMT_SEQ_C32)
 constexpr int SEQ_RING_SLOTS = 96;
-#endif
-#if !defined(SMT_ABL_OCC16)
-constexpr int SEQ_R = 96;     // ring entries: three 32-position chunks (span needed: 70 + SEQ_G)
+constexpr int SEQ_R = 96;     // three 32-position chunks, 24.6 KB per warp, 8 warps per SM: 0.91 ms per pass
+#else
+constexpr int SEQ_R = 72;     // ring entries: three 24-position chunks (span needed: 71) = 18.4 KB per warp, so that
+constexpr int SEQ_RING_SLOTS = 72;  // 12 warps fit per SM (3 per scheduler): 0.84 ms per pass
 #endif
 constexpr int SEQ_LOOK = 35;  // output j becomes computable when E[j+35] has been stored
-constexpr int SEQ_CH = 32;    // positions per chunk (one descriptor per lane)
+#if defined(SMT_SEQ_C32) || defined(SMT_ABL_OCC16)
+constexpr int SEQ_CH = 32;
+#else
+constexpr int SEQ_CH = 24;    // positions per chunk (one descriptor per lane, lanes 24-31 idle in the descriptor step)
+#endif
 // Measured on B200 at 1080p x 256 (ms per pass; 1.30 as shipped), see DESIGN.md 7:
 //   no loads and no stores 0.96, no stores 1.09, no loads 1.03: the walk is neither purely memory- nor issue-bound;
 //   16-position chunks, 80-entry ring, 10 warps/SM: 1.34;  one chunk in flight instead of two (127 registers): 1.33;
@@ -180,7 +185,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
         {   // DRAM -> L2 runs further ahead than the scoreboard allows registers to: ONE prefetch instruction per chunk, lane l
             // asks for the 128-byte row of position tb + (AHEAD + L2PF)*32 + l.  The register loads above then hit L2.
             const int q = tb + (SEQ_AHEAD + SMT_SEQ_L2PF) * SEQ_CH + lane;
-            if (q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
+            if ((SEQ_CH == 32 || lane < SEQ_CH) && q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
         }
 #endif
         const int jn = tb - SEQ_LOOK + lane + SEQ_CH;
@@ -274,11 +279,19 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 #endif
 }
 
-constexpr int SEQ_WARPS = 8;  // the 8 warps of a block walk the d-chunks of the same line(s): 1 KB contiguous per pixel
-constexpr int SEQ_SMEM_PER_WARP = SEQ_RING_SLOTS * 256 + SEQ_CH * (int)sizeof(Desc);
+#if defined(SMT_SEQ_C32) || defined(SMT_ABL_OCC16)
+constexpr int SEQ_WARPS = 8;
+#elif defined(SMT_SEQ_WARPS)
+constexpr int SEQ_WARPS = SMT_SEQ_WARPS;
+#else
+constexpr int SEQ_WARPS = 4;   // consecutive (line, d-chunk) tasks; three such blocks share an SM (12 warps), small blocks
+                               // keep small images spread over all SMs (12-warp blocks: equal at 1080p, 20 % slower at 450x375)
+#endif
+constexpr int SEQ_CTAS_PER_SM = 12 / SEQ_WARPS > 0 ? 12 / SEQ_WARPS : 1;
+constexpr int SEQ_SMEM_PER_WARP = SEQ_RING_SLOTS * 256;  // the descriptors live in a static array
 
 template <bool NONNEG, bool HAS_SUP, bool WTA, int CSTEP = 0>
-__global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
                                                      int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero, int tmaps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -532,6 +545,7 @@ static smt_status_t launch_seq2(smt_ctx* ctx, const float* in, float* out, const
 // the previous group of 8, handed over by shuffle) and in who touches memory (A lanes load, B lanes store; 64-byte rows).
 // With chunk base tb and step kk: A stores E_A[tb+kk] and emits j = tb+kk-35; B consumes A-output tb+kk-43, stores
 // E_B[tb+kk-43] in the slot of the same index (so E_B[q] lives at slot (q+43) mod 96) and emits i = tb+kk-78.
+constexpr int SEQH_CH = 32, SEQH_R = 96, SEQH_WARPS = 8;  // this kernel keeps 32-position chunks and a 96-entry ring
 constexpr int SEQH_LAG = SEQ_LOOK + SEQ_G;        // 43: B's prefix position trails A's by this much
 constexpr int SEQH_LOOKB = SEQH_LAG + SEQ_LOOK;   // 78: B's output position trails A's prefix position by this much
 struct PrefetchedH {
@@ -540,7 +554,7 @@ struct PrefetchedH {
 };
 
 template <bool NONNEG, bool EDGE>
-__device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (&rin)[SEQ_G], float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH],
+__device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (&rin)[SEQ_G], float (&vuse)[SEQH_CH], float (&vload)[SEQH_CH],
                                            int tb, int len, bool act, bool isb, const float* __restrict__ src_next,
                                            float* __restrict__ dst_first, long long step, long long pbase, long long pstride, int horiz,
                                            const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_col,
@@ -552,23 +566,23 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
         if (!EDGE || (ja >= 0 && ja < len)) {
             const unsigned aw = horiz ? (pre.armw_a & 0xffffu) : (pre.armw_a >> 16);
             const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            da.offa = (unsigned)(max(ja - lo, 0) % SEQ_R) * 256u;
-            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQ_R) * 256u;
+            da.offa = (unsigned)(max(ja - lo, 0) % SEQH_R) * 256u;
+            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQH_R) * 256u;
             da.cnt = (float)pre.cnt_a;
             da.rcp = __frcp_rn(da.cnt);
         }
         if (!EDGE || (ib >= 0 && ib < len)) {
             const unsigned aw = horiz ? (pre.armw_b & 0xffffu) : (pre.armw_b >> 16);
             const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            db.offa = (unsigned)((max(ib - lo, 0) + SEQH_LAG) % SEQ_R) * 256u;
-            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQH_LAG) % SEQ_R) * 256u;
+            db.offa = (unsigned)((max(ib - lo, 0) + SEQH_LAG) % SEQH_R) * 256u;
+            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQH_LAG) % SEQH_R) * 256u;
         }
         __syncwarp();
         desc[2 * lane] = da;  // interleaved so that the two halves of the warp read different banks
         desc[2 * lane + 1] = db;
         __syncwarp();
     }
-    unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;
+    unsigned char* wbase = ring_col + (unsigned)(tb % SEQH_R) * 256u;
     const Desc* dsel = desc + (isb ? 1 : 0);
     float* dp = dst_first;  // B output position tb - 78 (only B lanes store)
     *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);
@@ -577,20 +591,20 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
     {
         const float* p = src_next + dep;
 #pragma unroll
-        for (int k = 0; k < SEQ_CH; ++k) {
+        for (int k = 0; k < SEQH_CH; ++k) {
             if (EDGE)
-                vload[k] = (!isb && tb + SEQ_CH + k < len && act) ? __ldcs(p) : 0.f;
+                vload[k] = (!isb && tb + SEQH_CH + k < len && act) ? __ldcs(p) : 0.f;
             else
                 vload[k] = !isb ? __ldcs(p) : 0.f;
             p += step;
         }
 #if SMT_SEQ_L2PF > 0
         {
-            const int q = tb + (1 + SMT_SEQ_L2PF) * SEQ_CH + lane;
-            if (q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
+            const int q = tb + (1 + SMT_SEQ_L2PF) * SEQH_CH + lane;
+            if (q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQH_CH + lane)));
         }
 #endif
-        const int jn = tb - SEQ_LOOK + lane + SEQ_CH, in_ = tb - SEQH_LOOKB + lane + SEQ_CH;
+        const int jn = tb - SEQ_LOOK + lane + SEQH_CH, in_ = tb - SEQH_LOOKB + lane + SEQH_CH;
         pre.armw_a = pre.armw_b = 0u;
         pre.cnt_a = 1;
         if (jn >= 0 && jn < len) {
@@ -601,7 +615,7 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
         if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_ + dep);
     }
 #pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) {
+    for (int k = 0; k < SEQH_CH; ++k) {
         if (k > 0) {
             *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E_A[tb+k] / E_B[tb+k-43]
             acc = pre_add<NONNEG>(acc, isb ? rin[k & (SEQ_G - 1)] : vuse[k]);
@@ -632,16 +646,16 @@ __device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (
 }
 
 template <bool NONNEG>
-__global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seqh_kernel(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(SEQH_WARPS * 32) agg_seqh_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                  const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a, int H,
                                                                  int W, int D, int horiz, float bias_a, float bias_b, int zero) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* s_ring = smem_raw + (size_t)warp * (SEQ_R * 256 + 2 * SEQ_CH * (int)sizeof(Desc));
-    Desc* s_desc = reinterpret_cast<Desc*>(s_ring + SEQ_R * 256);
+    unsigned char* s_ring = smem_raw + (size_t)warp * (SEQH_R * 256 + 2 * SEQH_CH * (int)sizeof(Desc));
+    Desc* s_desc = reinterpret_cast<Desc*>(s_ring + SEQH_R * 256);
     const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
     const int nh = (D + 15) >> 4;  // 16-disparity groups per line
-    const long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
+    const long long wg = (long long)blockIdx.x * SEQH_WARPS + warp;
     const int line = (int)(wg / nh), hc = (int)(wg - (long long)line * nh);
     const int len = horiz ? W : H;
     if (line >= (horiz ? H : W)) return;
@@ -660,17 +674,17 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seqh_kernel(const float* _
     float rin[SEQ_G];
 #pragma unroll
     for (int u = 0; u < SEQ_G; ++u) rin[u] = 0.f;
-    float va[SEQ_CH], vb[SEQ_CH];
+    float va[SEQH_CH], vb[SEQH_CH];
 #pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) va[k] = (!isb && k < len && act) ? __ldcs(src + step * k) : 0.f;
+    for (int k = 0; k < SEQH_CH; ++k) va[k] = (!isb && k < len && act) ? __ldcs(src + step * k) : 0.f;
     PrefetchedH pre{0u, 0u, 1};
-    const int nouter = (len + SEQH_LOOKB + SEQ_CH - 1) / SEQ_CH;
+    const int nouter = (len + SEQH_LOOKB + SEQH_CH - 1) / SEQH_CH;
 #define SMT_SEQH_STEP(USE, LOAD)                                                                                              \
     if (o < nouter) {                                                                                                         \
-        const int tb = o * SEQ_CH;                                                                                            \
-        const float* src_next = src + step * (tb + SEQ_CH);                                                                   \
+        const int tb = o * SEQH_CH;                                                                                            \
+        const float* src_next = src + step * (tb + SEQH_CH);                                                                   \
         float* dst_first = dst + step * (tb - SEQH_LOOKB);                                                                    \
-        if (full && tb - SEQH_LOOKB >= 0 && tb + 2 * SEQ_CH <= len)                                                           \
+        if (full && tb - SEQH_LOOKB >= 0 && tb + 2 * SEQH_CH <= len)                                                           \
             seqh_chunk<NONNEG, false>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride, \
                                       horiz, arms, sup_a, ring_col, s_desc, lane, zero);                                      \
         else                                                                                                                  \
@@ -688,14 +702,14 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32) agg_seqh_kernel(const float* _
 template <bool NONNEG>
 static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
                                 int horiz, float bias_a, float bias_b) {
-    constexpr size_t smem = (size_t)SEQ_WARPS * (SEQ_R * 256 + 2 * SEQ_CH * sizeof(Desc));
+    constexpr size_t smem = (size_t)SEQH_WARPS * (SEQH_R * 256 + 2 * SEQH_CH * sizeof(Desc));
     static bool attr_set = false;
     if (!attr_set) {
         SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqh_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 15) / 16);
-    SMT_LAUNCH(ctx, (agg_seqh_kernel<NONNEG>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
+    SMT_LAUNCH(ctx, (agg_seqh_kernel<NONNEG>), cdiv(nwarps, SEQH_WARPS), SEQH_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
                bias_b, 0);
     return SMT_OK;
 }
