@@ -5,6 +5,8 @@
 //   first-minimum WTA of the aggregated right volume           (CrossArm.cpp:33; main.cpp:84)
 //   LeftRightConsistency, RemoveSpeckles, MedianFilter         (PostProcessing.h:72,250,314; main.cpp:92-94)
 // Everything stays on the device; only the two image pairs go in and disparity maps come out.
+#include <cstdlib>
+
 #include "common.cuh"
 
 extern "C" void smt_adcensus_default_params(smt_adcensus_params* p, int32_t rows, int32_t cols, int32_t D) {
@@ -101,11 +103,18 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     // ---- right view: cost -> aggregate -> WTA
     float* res = nullptr;
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 1, volA.as<float>(), nullptr, nullptr));
-    // (reducing to the disparity inside the last aggregation pass -- k_aggregate_cross's wta_disp -- was measured
-    //  slower than a separate streaming WTA: 22.3 vs 21.0 + 0.46 ms at 1080p x 256, so it is not used here)
-    SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
-                              2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res));
-    SMT_TRY(k_wta(ctx, res, H, W, D, dispR.as<float>()));
+    // Reducing to the disparity inside the last aggregation pass (k_aggregate_cross's wta_disp) saves one write and one
+    // read of the volume but adds a warp reduction per position to a kernel that is not memory-bound: measured 13.71 ms
+    // against 13.05 + 0.45 ms at 1080p x 256, so the separate streaming WTA stays the default (SMT_PIPE_FUSE_WTA=1 switches).
+    static const bool fuse_wta = getenv("SMT_PIPE_FUSE_WTA") != nullptr;
+    if (fuse_wta) {
+        SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
+                                  2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res, dispR.as<float>()));
+    } else {
+        SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
+                                  2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res));
+        SMT_TRY(k_wta(ctx, res, H, W, D, dispR.as<float>()));
+    }
 
     // ---- left view: cost -> aggregate -> 4-path scanline with fused WTA
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 0, volA.as<float>(), nullptr, nullptr));
