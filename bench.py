@@ -133,7 +133,28 @@ class ClockSampler:
         self.stop = threading.Event()
         self.thread = None
 
+    def _run_nvml(self):
+        """NVML polling (25 ms): enough samples inside a sub-second timed region.  Rows use the nvidia-smi layout."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self.stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx), "", hex(r)] + [("Active" if r & b else "Not Active") for _, b in bits])
+            self.stop.wait(0.025)
+        nv.nvmlShutdown()
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],

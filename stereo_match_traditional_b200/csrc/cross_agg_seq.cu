@@ -59,6 +59,20 @@ constexpr int SEQ_CH = 24;    // positions per chunk (one descriptor per lane, l
 #define SMT_SEQ_L2PF 2  // chunks between the register loads and the L2 prefetch running ahead of them (0 = no prefetch)
 #endif
 constexpr int SEQ_AHEAD = SMT_SEQ_AHEAD;  // chunks of input in flight per warp (register buffers = SEQ_AHEAD + 1)
+#ifndef SMT_SEQ_ST
+#define SMT_SEQ_ST 0
+#endif
+__device__ __forceinline__ void seq_store(float* p, float v) {  // cache policy of the volume stores (0 = streaming)
+#if SMT_SEQ_ST == 0
+    __stcs(p, v);
+#elif SMT_SEQ_ST == 1
+    *p = v;
+#elif SMT_SEQ_ST == 2
+    __stcg(p, v);
+#else
+    __stwt(p, v);
+#endif
+}
 #ifndef SMT_SEQ_PIPE
 #define SMT_SEQ_PIPE 1
 #endif
@@ -235,7 +249,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
 #if defined(SMT_ABL_NOSTORE)
                     if (r == 123456.f)
 #endif
-                    __stcs(reinterpret_cast<float*>(dp), r);
+                    seq_store(reinterpret_cast<float*>(dp), r);
                 }
                 dp += step_b;
                 wp += wta_step;
