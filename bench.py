@@ -302,7 +302,11 @@ def gpu_arm(args, H, W, D):
                 "launches_per_frame": nlaunch[dom], "algorithmic_bytes_per_frame": alg[dom], "stage_ms_per_frame": st[dom],
                 "all_stages": {k: {"ms_per_frame": st.get(k, 0.0), "algorithmic_GBps": (alg[k] / (st[k] / 1e3) / 1e9) if st.get(k) else None}
                                for k in alg},
-                "other_stage_ms_per_frame": {k: v for k, v in st.items() if k not in alg}}
+                "other_stage_ms_per_frame": {k: v for k, v in st.items() if k not in alg},
+                # SURVEY.md 8(d) asks for both denominators and for the whole frame's compulsory traffic (22 V)
+                "peak_nominal": 8000.0, "frac_of_nominal": ach / 8000.0,
+                "frame": {"algorithmic_bytes": sum(alg.values()), "achieved": sum(alg.values()) * fps / world / 1e9,
+                          "frac": sum(alg.values()) * fps / world / 1e9 / peak}}
 
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
