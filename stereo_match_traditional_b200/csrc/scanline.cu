@@ -266,11 +266,14 @@ smt_status_t k_scanline(smt_ctx* ctx, const float* cost, const float* gray, int 
             break;
         }
     }
+#ifndef SMT_SCAN_PF8
+#define SMT_SCAN_PF8 6  // ring depth (steps) of the DPL = 8, float4 kernel, the 1080p x 256 case
+#endif
 #define SMT_SCAN_CASE(DPL_, VW_, PF_) \
     if (dpl == DPL_ && vw == VW_)     \
         return launch_paths<DPL_, VW_, PF_>(ctx, cost, gray, H, W, D, fp1, fp2, left, right, up, down, sum, disp, scratch);
     SMT_SCAN_CASE(16, 4, 2)
-    SMT_SCAN_CASE(8, 4, 4)
+    SMT_SCAN_CASE(8, 4, SMT_SCAN_PF8)
     SMT_SCAN_CASE(4, 4, 4)
     SMT_SCAN_CASE(16, 2, 2)
     SMT_SCAN_CASE(8, 2, 4)
