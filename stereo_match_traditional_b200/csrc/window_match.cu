@@ -220,13 +220,19 @@ __global__ void __launch_bounds__(256) ncc_select_kernel(const int* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- ASW
-constexpr int ASW_TX = 4, ASW_TD = 64;
+constexpr int ASW_TX = 4, ASW_TD = 32, ASW_Q = 4;  // columns per block, disparity lanes, disparities per lane
 
 // Lp/Rp: replicate-padded grey [Hp][Wp], pad = wins = winSize+1 (ASWeight.cpp:54-55).  One block per (output row,
-// ASW_TX columns); thread = (column, disparity lane).  cost = sum(wOwn*wOth*min(|a-b|,T)) / sum(wOwn*wOth) with
-// w = colour[|p - centre|] * space[tap] (ASW.h:210-257); first-minimum WTA (:193-208).
+// ASW_TX columns); thread = (column, disparity lane), each lane owns ASW_Q consecutive disparities.
+// cost = sum(wOwn*wOth*min(|a-b|,T)) / sum(wOwn*wOth) with w = colour[|p - centre|] * space[tap] (ASW.h:210-257), taps
+// accumulated in the reference's row-major order per cell; first-minimum WTA (:193-208).
+// The four windows of a lane in the other image are one pixel apart, so along a tap row they slide through a 4-deep
+// register window (one new byte per tap instead of four), and the own pixel, spatial weight and own-window weight of a
+// tap are read once for four cells.  The colour table is replicated per lane (index v*32 + lane): the lookups are
+// data-dependent and would otherwise collide in the banks.
+template <bool RIGHT>
 __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __restrict__ own_img, const uint8_t* __restrict__ oth_img,
-                                                              int Hp, int Wp, int wins, int D, int T, int right_view,
+                                                              int Hp, int Wp, int wins, int D, int T,
                                                               const float* __restrict__ space, const float* __restrict__ color,
                                                               float* __restrict__ disp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -234,18 +240,18 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
     const int Wo = Wp - 2 * wins;
     const int own_w = ASW_TX + k - 1, oth_w = ASW_TX + k - 1 + D - 1;
     float* s_space = reinterpret_cast<float*>(smem_raw);       // [kk]
-    float* s_color = s_space + kk;                             // [256]
-    float* s_wown = s_color + 256;                             // [ASW_TX][kk]
+    float* s_colr = s_space + kk;                              // [256][32]
+    float* s_wown = s_colr + 256 * 32;                         // [ASW_TX][kk]
     float* s_bestv = s_wown + ASW_TX * kk;                     // [ASW_TX][ASW_TD]
     int* s_bestd = reinterpret_cast<int*>(s_bestv + ASW_TX * ASW_TD);
     uint8_t* s_own = reinterpret_cast<uint8_t*>(s_bestd + ASW_TX * ASW_TD);  // [k][own_w]
     uint8_t* s_oth = s_own + (size_t)k * own_w;                             // [k][oth_w]
 
     const int io = blockIdx.y, jo0 = blockIdx.x * ASW_TX;
-    const int tid = threadIdx.x, xl = tid / ASW_TD, dl = tid % ASW_TD;
-    const int oth_base = right_view ? jo0 : jo0 - (D - 1);  // padded column of s_oth[.][0]
+    const int tid = threadIdx.x, xl = tid / ASW_TD, dl = tid % ASW_TD, l32 = tid & 31;
+    const int oth_base = RIGHT ? jo0 : jo0 - (D - 1);  // padded column of s_oth[.][0]
     for (int t = tid; t < kk; t += blockDim.x) s_space[t] = space[t];
-    for (int t = tid; t < 256; t += blockDim.x) s_color[t] = color[t];
+    for (int t = tid; t < 256 * 32; t += blockDim.x) s_colr[t] = color[t >> 5];
     for (int t = tid; t < k * own_w; t += blockDim.x) {
         const int r = t / own_w, c = t - r * own_w;
         const int x = jo0 + c;
@@ -262,38 +268,77 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
         const int x = t / kk, tap = t - x * kk;
         const int r = tap / k, c = tap - r * k;
         const int centre = s_own[(size_t)wins * own_w + x + wins];
-        s_wown[t] = __fmul_rn(s_color[abs((int)s_own[(size_t)r * own_w + x + c] - centre)], s_space[tap]);
+        s_wown[t] = __fmul_rn(color[abs((int)s_own[(size_t)r * own_w + x + c] - centre)], s_space[tap]);
     }
     __syncthreads();
 
     const int jo = jo0 + xl;
+    const float* colr = s_colr + l32;
     float bestv = INFINITY;
     int bestd = 0x7fffffff;
-    for (int d = dl; d < D; d += ASW_TD) {
-        const bool valid = right_view ? (jo + d < Wo - wins - 1) : (jo - d >= 0);
-        if (jo >= Wo || !valid) continue;
-        const int off = right_view ? xl + d : xl + (D - 1 - d);  // column of the other window's left edge in s_oth
-        const int cb = s_oth[(size_t)wins * oth_w + off + wins];
+    for (int d0 = dl * ASW_Q; d0 < D; d0 += ASW_TD * ASW_Q) {
+        if (jo >= Wo) break;
+        // column (in s_oth) of the left edge of the window of disparity d0 + i: RIGHT: xl + d0 + i, else xl + D-1 - d0 - i
+        const int off0 = RIGHT ? xl + d0 : xl + (D - 1 - d0);
+        int cb[ASW_Q];
+#pragma unroll
+        for (int i = 0; i < ASW_Q; ++i) {
+            const int o = min(max(RIGHT ? off0 + i : off0 - i, 0), oth_w - k);
+            cb[i] = s_oth[(size_t)wins * oth_w + o + wins];
+        }
         const float* wo = s_wown + xl * kk;
-        float sw = 0.f, sv = 0.f;
+        float sw[ASW_Q], sv[ASW_Q];
+#pragma unroll
+        for (int i = 0; i < ASW_Q; ++i) sw[i] = sv[i] = 0.f;
         for (int r = 0; r < k; ++r) {
             const uint8_t* a = s_own + (size_t)r * own_w + xl;
-            const uint8_t* b = s_oth + (size_t)r * oth_w + off;
+            const uint8_t* b = s_oth + (size_t)r * oth_w;
             const float* sp = s_space + r * k;
             const float* w0 = wo + r * k;
+            // pb[i] = other-image pixel of cell i at the current tap column
+            int pb[ASW_Q];
+#pragma unroll
+            for (int i = 1; i < ASW_Q; ++i) {
+                // the three values that slide in from the previous columns (clamped: cells outside the range are discarded)
+                const int idx = RIGHT ? off0 + i - 1 : off0 - i;
+                pb[RIGHT ? i - 1 : i] = b[min(max(idx, 0), oth_w - 1)];
+            }
             for (int c = 0; c < k; ++c) {
-                const int pa = a[c], pb = b[c];
-                const float m1 = __fmul_rn(s_color[abs(pb - cb)], sp[c]);
-                const float m2 = __fmul_rn(w0[c], m1);
-                const int e = min(abs(pa - pb), T);
-                sw = __fadd_rn(sw, m2);
-                sv = __fadd_rn(sv, __fmul_rn(m2, (float)e));
+                const int pa = a[c];
+                const float spc = sp[c], w0c = w0[c];
+                if (RIGHT) {
+                    pb[ASW_Q - 1] = b[min(off0 + ASW_Q - 1 + c, oth_w - 1)];
+                } else {
+                    pb[0] = b[off0 + c];
+                }
+#pragma unroll
+                for (int i = 0; i < ASW_Q; ++i) {
+                    const float m1 = __fmul_rn(colr[abs(pb[i] - cb[i]) * 32], spc);
+                    const float m2 = __fmul_rn(w0c, m1);
+                    const int e = min(abs(pa - pb[i]), T);
+                    sw[i] = __fadd_rn(sw[i], m2);
+                    sv[i] = __fadd_rn(sv[i], __fmul_rn(m2, (float)e));
+                }
+                if (RIGHT) {
+#pragma unroll
+                    for (int i = 0; i < ASW_Q - 1; ++i) pb[i] = pb[i + 1];
+                } else {
+#pragma unroll
+                    for (int i = ASW_Q - 1; i > 0; --i) pb[i] = pb[i - 1];
+                }
             }
         }
-        const float cost = __fdiv_rn(sv, sw);
-        if (cost < bestv) {  // ascending d inside the thread: strict '<' keeps the first minimum
-            bestv = cost;
-            bestd = d;
+#pragma unroll
+        for (int i = 0; i < ASW_Q; ++i) {
+            const int d = d0 + i;
+            const bool valid = d < D && (RIGHT ? (jo + d < Wo - wins - 1) : (jo - d >= 0));
+            if (valid) {
+                const float cost = __fdiv_rn(sv[i], sw[i]);
+                if (cost < bestv) {  // ascending d inside the thread: strict '<' keeps the first minimum
+                    bestv = cost;
+                    bestd = d;
+                }
+            }
         }
     }
     s_bestv[tid] = bestv;
@@ -405,7 +450,7 @@ smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     SMT_CUDA(ctx, cudaSetDevice(ctx->device));
     const int Ho = rows_padded - 2 * wins, Wo = cols_padded - 2 * wins;
     const size_t np = (size_t)rows_padded * cols_padded, no = (size_t)Ho * Wo;
-    const size_t smem = sizeof(float) * ((size_t)k * k + 256 + (size_t)ASW_TX * k * k + ASW_TX * ASW_TD) + sizeof(int) * ASW_TX * ASW_TD +
+    const size_t smem = sizeof(float) * ((size_t)k * k + 256 * 32 + (size_t)ASW_TX * k * k + ASW_TX * ASW_TD) + sizeof(int) * ASW_TX * ASW_TD +
                         (size_t)k * (ASW_TX + k - 1) + (size_t)k * (ASW_TX + k - 1 + D - 1);
     SMT_REQUIRE(ctx, smem <= 200 * 1024, SMT_ERR_UNSUPPORTED, "smt_asw: window / disparity range too large for the shared-memory tile");
     Marshal ms(ctx, space);
@@ -423,12 +468,19 @@ smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     SMT_ALLOC(ctx, masks, h.size() * sizeof(float));
     SMT_CUDA(ctx, cudaMemcpyAsync(masks.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h is a local vector
-    if (smem > 48 * 1024) SMT_CUDA(ctx, cudaFuncSetAttribute(asw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        SMT_CUDA(ctx, cudaFuncSetAttribute(asw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(asw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     {
         StageTimer t(ctx, ST_COST);
         dim3 grid(cdiv(Wo, ASW_TX), Ho);
-        SMT_LAUNCH(ctx, asw_kernel, grid, ASW_TX * ASW_TD, smem, right_view ? dr : dl, right_view ? dl : dr, rows_padded, cols_padded, wins, D,
-                   T, right_view ? 1 : 0, masks.as<float>(), masks.as<float>() + (size_t)k * k, dd);
+        if (right_view)
+            SMT_LAUNCH(ctx, asw_kernel<true>, grid, ASW_TX * ASW_TD, smem, dr, dl, rows_padded, cols_padded, wins, D, T, masks.as<float>(),
+                       masks.as<float>() + (size_t)k * k, dd);
+        else
+            SMT_LAUNCH(ctx, asw_kernel<false>, grid, ASW_TX * ASW_TD, smem, dl, dr, rows_padded, cols_padded, wins, D, T, masks.as<float>(),
+                       masks.as<float>() + (size_t)k * k, dd);
     }
     return ms.finish();
 }
