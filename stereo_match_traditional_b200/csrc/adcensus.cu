@@ -107,7 +107,9 @@ constexpr int COST_TJ = 32;
 
 // grid (ceil(W/TJ), H), 256 threads.  Each block stages the TJ own strings/masks/values and the D+TJ+2 "other image"
 // strings/values one row needs, then streams TJ*D cost cells with float4 stores (VEC=4) -- D innermost, coalesced.
-template <int VEC>
+// PARTS: also write the AD and Hamming volumes (the int -> float conversions they need run at a quarter of the FP32 rate,
+// so the cost-only instantiation does not even compute them).
+template <int VEC, bool PARTS>
 __global__ void __launch_bounds__(256)
     adcensus_cost_kernel(const uint8_t* __restrict__ own_img, const uint8_t* __restrict__ oth_img,
                          const uint64_t* __restrict__ Cown, const uint64_t* __restrict__ Cext,
@@ -169,19 +171,21 @@ __global__ void __launch_bounds__(256)
             const uint64_t e = s_ext[skew(q)];
             const int a = abs(v0 - (int)s_oth[q]);
             const int h = __popcll((c0 ^ e) & m);
-            oa[k] = (float)a;
-            oh[k] = (float)h;
+            if (PARTS) {
+                oa[k] = (float)a;
+                oh[k] = (float)h;
+            }
             oc[k] = __fadd_rn(s_lut[a], s_lut[256 + h]);
         }
         const size_t o = ((size_t)i * W + j) * D + (size_t)dg * VEC;
         if (VEC == 4) {
             __stcs(reinterpret_cast<float4*>(cost + o), make_float4(oc[0], oc[1], oc[2], oc[3]));
-            if (ad) __stcs(reinterpret_cast<float4*>(ad + o), make_float4(oa[0], oa[1], oa[2], oa[3]));
-            if (census) __stcs(reinterpret_cast<float4*>(census + o), make_float4(oh[0], oh[1], oh[2], oh[3]));
+            if (PARTS && ad) __stcs(reinterpret_cast<float4*>(ad + o), make_float4(oa[0], oa[1], oa[2], oa[3]));
+            if (PARTS && census) __stcs(reinterpret_cast<float4*>(census + o), make_float4(oh[0], oh[1], oh[2], oh[3]));
         } else {
             cost[o] = oc[0];
-            if (ad) ad[o] = oa[0];
-            if (census) census[o] = oh[0];
+            if (PARTS && ad) ad[o] = oa[0];
+            if (PARTS && census) census[o] = oh[0];
         }
     }
 }
@@ -200,22 +204,26 @@ smt_status_t k_adcensus_cost(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, c
     const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0) &&
                       (!ad || (reinterpret_cast<uintptr_t>(ad) & 15) == 0) &&
                       (!census || (reinterpret_cast<uintptr_t>(census) & 15) == 0);
-    if (smem > 48 * 1024) {
-        SMT_CUDA(ctx, cudaFuncSetAttribute(adcensus_cost_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMT_CUDA(ctx, cudaFuncSetAttribute(adcensus_cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    if (vec4)
-        SMT_LAUNCH(ctx, adcensus_cost_kernel<4>, grid, 256, smem, own, oth, Cown, Cext, m.M, ctx->d_lut, H, W, D, view, nmax,
-                   cost, ad, census);
-    else
-        SMT_LAUNCH(ctx, adcensus_cost_kernel<1>, grid, 256, smem, own, oth, Cown, Cext, m.M, ctx->d_lut, H, W, D, view, nmax,
-                   cost, ad, census);
+    const bool parts = ad != nullptr || census != nullptr;
+#define SMT_COST_LAUNCH(VEC_, PARTS_)                                                                                                \
+    do {                                                                                                                             \
+        if (smem > 48 * 1024)                                                                                                        \
+            SMT_CUDA(ctx, cudaFuncSetAttribute(adcensus_cost_kernel<VEC_, PARTS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SMT_LAUNCH(ctx, (adcensus_cost_kernel<VEC_, PARTS_>), grid, 256, smem, own, oth, Cown, Cext, m.M, ctx->d_lut, H, W, D, view, nmax, \
+                   cost, ad, census);                                                                                                \
+    } while (0)
+    if (vec4 && parts) SMT_COST_LAUNCH(4, true);
+    else if (vec4) SMT_COST_LAUNCH(4, false);
+    else if (parts) SMT_COST_LAUNCH(1, true);
+    else SMT_COST_LAUNCH(1, false);
+#undef SMT_COST_LAUNCH
     return SMT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- WTA
 // One warp per pixel; lane l scans d = l, l+32, ... (coalesced 128 B per step) keeping its first minimum, then the
 // warp reduces (value, d) lexicographically, which is the reference's strict-'>' first minimum (AD-Census.h:359-372).
+template <bool VEC4>
 __global__ void __launch_bounds__(256) wta_first_min_kernel(const float* __restrict__ vol, size_t npix, int D,
                                                             float* __restrict__ disp) {
     const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -224,11 +232,25 @@ __global__ void __launch_bounds__(256) wta_first_min_kernel(const float* __restr
     const float* p = vol + pix * D;
     float best = INFINITY;
     int bd = 0x7fffffff;
-    for (int d = lane; d < D; d += 32) {
-        float v = __ldcs(p + d);
-        if (v < best || bd == 0x7fffffff) {
-            best = v;
-            bd = d;
+    if (VEC4) {
+        // lane l owns d = 4l .. 4l+3 (+128, ...): 512 bytes per warp and request, ascending d inside the lane
+        for (int d = lane * 4; d < D; d += 128) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(p + d));
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (e[k] < best || bd == 0x7fffffff) {
+                    best = e[k];
+                    bd = d + k;
+                }
+        }
+    } else {
+        for (int d = lane; d < D; d += 32) {
+            float v = __ldcs(p + d);
+            if (v < best || bd == 0x7fffffff) {
+                best = v;
+                bd = d;
+            }
         }
     }
 #pragma unroll
@@ -246,7 +268,10 @@ __global__ void __launch_bounds__(256) wta_first_min_kernel(const float* __restr
 smt_status_t k_wta(smt_ctx* ctx, const float* vol, int H, int W, int D, float* disp) {
     StageTimer t(ctx, ST_WTA);
     size_t npix = (size_t)H * W;
-    SMT_LAUNCH(ctx, wta_first_min_kernel, cdiv((long long)npix, 8), 256, 0, vol, npix, D, disp);
+    if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0)
+        SMT_LAUNCH(ctx, wta_first_min_kernel<true>, cdiv((long long)npix, 8), 256, 0, vol, npix, D, disp);
+    else
+        SMT_LAUNCH(ctx, wta_first_min_kernel<false>, cdiv((long long)npix, 8), 256, 0, vol, npix, D, disp);
     return SMT_OK;
 }
 
