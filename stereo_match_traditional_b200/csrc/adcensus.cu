@@ -103,7 +103,10 @@ smt_status_t k_ensure_lut(smt_ctx* ctx, float sigmaC, float sigmaS) {
 // stride: 4-way bank conflicts.  Skewing by q>>2 turns the stride into 5 eight-byte words, coprime with 16.
 __device__ __forceinline__ int skew(int q) { return q + (q >> 2); }
 
-constexpr int COST_TJ = 32;
+#ifndef SMT_COST_TJ
+#define SMT_COST_TJ 128  // pixels per block: the D+TJ staged strings are amortised over TJ*D cells (32: 1.21 ms, 128: 1.11 ms per frame)
+#endif
+constexpr int COST_TJ = SMT_COST_TJ;
 
 // grid (ceil(W/TJ), H), 256 threads.  Each block stages the TJ own strings/masks/values and the D+TJ+2 "other image"
 // strings/values one row needs, then streams TJ*D cost cells with float4 stores (VEC=4) -- D innermost, coalesced.
