@@ -38,14 +38,15 @@ void census_maps_carve(void* base, int H, int W, CensusMaps* m) {
 enum { CM_OWN = 0, CM_RIGHT_EXT = 1, CM_LEFT_EXT = 2, CM_MASK = 3 };
 
 // One thread per (row, column slot) of one map.
-__global__ void __launch_bounds__(256) census_map_kernel(const uint8_t* __restrict__ img, int H, int W, int ncol, int mode,
+template <int mode>
+__global__ void __launch_bounds__(256) census_map_kernel(const uint8_t* __restrict__ img, int H, int W, int ncol,
                                                          uint64_t* __restrict__ out) {
     int xi = blockIdx.x * blockDim.x + threadIdx.x;
     int i = blockIdx.y;
     if (xi >= ncol) return;
     const int xv = (mode == CM_RIGHT_EXT) ? xi - 3 : xi;  // virtual column
     int cc = xv < 0 ? 0 : (xv > W - 1 ? W - 1 : xv);
-    const int centre = img[(size_t)i * W + cc];
+    const int centre = mode == CM_MASK ? 0 : img[(size_t)i * W + cc];
     uint64_t v = 0;
 #pragma unroll
     for (int r = -4; r <= 4; ++r) {
@@ -78,11 +79,11 @@ __global__ void __launch_bounds__(256) census_map_kernel(const uint8_t* __restri
 smt_status_t k_census_maps(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, int H, int W, const CensusMaps& m) {
     StageTimer t(ctx, ST_CENSUS);
     dim3 blk(128);
-    SMT_LAUNCH(ctx, census_map_kernel, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, CM_OWN, m.CL);
-    SMT_LAUNCH(ctx, census_map_kernel, dim3(cdiv(W, 128), H), blk, 0, R, H, W, W, CM_OWN, m.CR);
-    SMT_LAUNCH(ctx, census_map_kernel, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, CM_MASK, m.M);
-    SMT_LAUNCH(ctx, census_map_kernel, dim3(cdiv(W + 3, 128), H), blk, 0, R, H, W, W + 3, CM_RIGHT_EXT, m.CRx);
-    SMT_LAUNCH(ctx, census_map_kernel, dim3(cdiv(W + 4, 128), H), blk, 0, L, H, W, W + 4, CM_LEFT_EXT, m.CLx);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, m.CL);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(W, 128), H), blk, 0, R, H, W, W, m.CR);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_MASK>, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, m.M);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_RIGHT_EXT>, dim3(cdiv(W + 3, 128), H), blk, 0, R, H, W, W + 3, m.CRx);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_LEFT_EXT>, dim3(cdiv(W + 4, 128), H), blk, 0, L, H, W, W + 4, m.CLx);
     return SMT_OK;
 }
 
@@ -325,7 +326,7 @@ smt_status_t smt_census9x7_u64(smt_ctx* ctx, const float* img, int32_t rows, int
     SMT_TRY(k_f32_to_u8(ctx, di, npix, u8.as<uint8_t>()));
     {
         StageTimer t(ctx, ST_CENSUS);
-        SMT_LAUNCH(ctx, census_map_kernel, dim3(cdiv(cols, 128), rows), 128, 0, u8.as<uint8_t>(), rows, cols, cols, CM_OWN, dout);
+        SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(cols, 128), rows), 128, 0, u8.as<uint8_t>(), rows, cols, cols, dout);
     }
     return ms.finish();
 }
