@@ -3,16 +3,18 @@
 // A pass along a line is out[j] = E[j+hi(j)+1] - E[j-lo(j)] with E the exclusive prefix of the line and lo, hi <= 34
 // the pixel's arms (cross_aggregator.cpp:353-389).  Because the arms are bounded, an output only ever needs prefix
 // entries within [j-34, j+35]: a warp walks the line ONCE, keeps the running compensated prefix in registers and the
-// last 96 entries in a shared-memory ring, and emits output j as soon as the prefix has reached j+35.
+// last 72 entries in a shared-memory ring, and emits output j as soon as the prefix has reached j+35.
 //   * lane = disparity: every load / store is a 128-byte row of the [H][W][D] volume; arms, support counts and ring
-//     slots are warp-uniform, prepared 32 positions at a time (one per lane) and read back as broadcast LDS;
-//   * no tiles: no halo re-reads, no segment totals, no block barriers -- the ring is lane-private storage;
-//   * the ring has 96 = 3*32 slots and chunks are 32 positions, so inside a chunk every ring store has a compile-time
+//     slots are warp-uniform, prepared one chunk (24 positions, one per lane) at a time and read back as broadcast LDS;
+//   * no tiles: no halo re-reads, no segment totals, no block barriers -- the ring is lane-private storage, 18.4 KB per
+//     warp, which is what lets 12 warps share an SM;
+//   * the ring has 72 = 3*24 slots and chunks are 24 positions, so inside a chunk every ring store has a compile-time
 //     offset; the interior chunks of a line run a predicate-free path;
+//   * a chunk is ordered around the ONE scoreboard ptxas gives all global loads (see seq_chunk): consume what the
+//     previous chunk fetched, then issue this chunk's loads, then compute; DRAM -> L2 runs two chunks further ahead with
+//     one prefetch instruction per chunk; descriptor and ring reads are software-pipelined over the positions;
 //   * per cell: 4 FADD (prefix) + 3 FADD (difference) + 3 FMA-class ops for the exact division + 1 STS.64 + 3 LDS + 1 LDG +
-//     1 STG + ~6 integer ops, against ~65 instructions for the tiled kernel in cross_agg_fast.cu;
-//   * input rows are prefetched two chunks (8 KB per warp) ahead in rotating register buffers.  (L2 prefetch
-//     instructions -- prefetch.global.L2 and cp.async.bulk.prefetch.L2 -- were measured: no gain / slower.)
+//     1 STG + ~4 integer ops, against ~65 instructions for the tiled kernel in cross_agg_fast.cu.
 // Numerics are those of cross_agg_fast.cu: cascaded compensated prefix (s, c) for non-negative input (a power-of-two
 // bias keeps the FastTwoSum error term exact), general TwoSum pair otherwise; window sums are exact to ~2^-46 and
 // rounded once.  The division by the support count is the correctly rounded quotient (Markstein's residual step on the
@@ -45,13 +47,10 @@ constexpr int SEQ_CH = 32;
 #else
 constexpr int SEQ_CH = 24;    // positions per chunk (one descriptor per lane, lanes 24-31 idle in the descriptor step)
 #endif
-// Measured on B200 at 1080p x 256 (ms per pass; 1.30 as shipped), see DESIGN.md 7:
-//   no loads and no stores 0.96, no stores 1.09, no loads 1.03: the walk is neither purely memory- nor issue-bound;
-//   16-position chunks, 80-entry ring, 10 warps/SM: 1.34;  one chunk in flight instead of two (127 registers): 1.33;
-//   16 warps/SM (timing-only run with a truncated ring): 1.22;  descriptor/ring reads software-pipelined by hand: 1.36
-//   (ncu: short-scoreboard stalls 19 -> 12 %, but the larger code raised instruction-cache stalls 7 -> 14 %);
-//   compile-time position step for horizontal passes (-27 % instructions in those passes): 1.29;
-//   arm words / support counts fetched two chunks ahead instead of one (6 % of the stall samples sit on their first use): 1.31.
+// Measured on B200 at 1080p x 256, ms per pass (history in DESIGN.md 4): 1.30 with the loads issued at the top of a chunk
+// (every chunk then waited for its own loads); 1.18 with the order below; 1.03 with the L2 prefetch; 0.93 with the
+// software-pipelined shared-memory reads; 0.82 with 24-position chunks and 12 warps per SM.  Flat at this point: prefetch
+// distance 1-6 chunks, lags 3-6, one or two chunks in flight, store cache policy, block size 2-12 warps.
 #ifndef SMT_SEQ_AHEAD
 #define SMT_SEQ_AHEAD 1
 #endif
