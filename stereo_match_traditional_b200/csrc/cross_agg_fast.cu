@@ -242,7 +242,8 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
         passes.push_back({!hfirst, hfirst ? sup0 : sup1});
         hfirst = !hfirst;
     }
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // function attributes are per device
+    bool& attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<1>::SMEM));
         SMT_CUDA(ctx, cudaFuncSetAttribute(agg_line_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AggCfg<2>::SMEM));

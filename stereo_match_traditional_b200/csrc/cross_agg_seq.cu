@@ -539,7 +539,8 @@ template <bool NONNEG>
 static smt_status_t launch_seq2(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
                                 int horiz, float bias_a, float bias_b) {
     constexpr size_t smem = (size_t)SEQ2_WARPS * SEQ2_SMEM_PER_WARP;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // function attributes are per device
+    bool& attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq2_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -716,7 +717,8 @@ template <bool NONNEG>
 static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
                                 int horiz, float bias_a, float bias_b) {
     constexpr size_t smem = (size_t)SEQH_WARPS * (SEQH_R * 256 + 2 * SEQH_CH * sizeof(Desc));
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // function attributes are per device
+    bool& attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqh_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -731,18 +733,25 @@ template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
                                int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0) {
     constexpr size_t smem = (size_t)SEQ_WARPS * SEQ_SMEM_PER_WARP;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // function attributes are per device
+    bool& attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // three blocks per SM need 225 of the 228 KB: ask for the largest shared-memory carve-out explicitly
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP, WTA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
     // horizontal walk of a 256-disparity volume (the benchmark shape): the position step is a compile-time constant, so
     // the 32 loads and 32 stores of a chunk use immediate offsets from one base register (-27 % instructions, +1.3 %)
     if constexpr (NONNEG && !WTA) if (horiz && D == 256) {
-        static bool attr2 = false;
+        static bool attr2_dev[64] = {};
+        bool& attr2 = attr2_dev[ctx->device & 63];
         if (!attr2) {
             SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               (int)cudaSharedmemCarveoutMaxShared));
             attr2 = true;
         }
         SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
