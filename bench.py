@@ -237,9 +237,9 @@ def gpu_arm(args, H, W, D):
 
     def step_host():
         outs = []
-        for fr in pin_frames:
+        for fr, po in zip(pin_frames, pin_out):
             outs.append(eng.pipeline(fr["bgr_left"].numpy(), fr["bgr_right"].numpy(), D, fr["gray_left"].numpy(),
-                                     fr["gray_right"].numpy(), params=params)["disp"])
+                                     fr["gray_right"].numpy(), params=params, out=po.numpy())["disp"])
         return outs
 
     def barrier():

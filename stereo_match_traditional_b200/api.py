@@ -466,8 +466,10 @@ class Engine:
         return p
 
     def pipeline(self, bgr_left, bgr_right, D, gray_left=None, gray_right=None, params: Optional[AdCensusParams] = None,
-                 want: Sequence[str] = ("disp",), **overrides):
-        """P_full.  ``want`` from {"disp", "left_raw", "right_raw", "lrc"}; keyword overrides set params fields."""
+                 want: Sequence[str] = ("disp",), out=None, **overrides):
+        """P_full.  ``want`` from {"disp", "left_raw", "right_raw", "lrc"}; keyword overrides set params fields.
+        ``out``: optional caller-owned float32 [H, W] array for the final disparity (host memspace: e.g. a pinned buffer,
+        like the reference's caller-owned output arrays)."""
         a = _Args(self, bgr_left, bgr_right)
         H, W = bgr_left.shape[:2]
         p = params or self.default_params(H, W, D)
@@ -479,7 +481,12 @@ class Engine:
         pbr = a.inp(bgr_right, np.uint8, (H, W, 3))
         pgl = a.inp(gray_left, np.uint8, (H, W))
         pgr = a.inp(gray_right, np.uint8, (H, W))
-        disp, pd = a.out((H, W), np.float32)
+        if out is not None and not a.device:
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (H, W) and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous float32 [H, W] numpy array")
+            disp, pd = out, C.c_void_p(out.ctypes.data)
+        else:
+            disp, pd = a.out((H, W), np.float32)
         lraw, p1 = a.out((H, W), np.float32, "left_raw" in want)
         rraw, p2 = a.out((H, W), np.float32, "right_raw" in want)
         lrc, p3 = a.out((H, W), np.float32, "lrc" in want)

@@ -226,3 +226,15 @@ def test_pipeline_degenerate_shapes(engine, oracle, H, W, D):
     fast = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=names, sum_mode=SUM_FAST)
     for n in ("left_raw", "right_raw"):
         assert (fast[n] == ref[n]).mean() >= 0.99 and np.abs(fast[n] - ref[n]).max() <= 1, n   # few pixels: 1 % = a handful
+
+
+def test_pipeline_caller_owned_output(engine, oracle):
+    """`out=`: the disparity map lands in the caller's array (the reference's caller-owned output convention)."""
+    H, W, D = 40, 112, 16
+    p = make_pair(H, W, D, 5, "scene")
+    ref = oracle_pfull(oracle, p, D)
+    buf = np.full((H, W), -7.0, np.float32)
+    got = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], out=buf)
+    assert got["disp"] is buf and np.array_equal(buf, ref["disp"], equal_nan=True)
+    with pytest.raises(ValueError):
+        engine.pipeline(p["bgr_left"], p["bgr_right"], D, out=np.zeros((H, W + 1), np.float32))
