@@ -225,7 +225,7 @@ smt_status_t k_transpose_maps(smt_ctx* ctx, const uint8_t* arms8, const uint16_t
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
                             int horiz, bool nonneg, float bias, int tmaps);  // cross_agg_seq.cu
 smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
-                            int horiz, bool nonneg, float bias_a, float bias_b);
+                            int horiz, bool nonneg, float bias_a, float bias_b, int tmaps);
 smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D, int horiz,
                                 float bias, float* disp);
 
@@ -261,6 +261,7 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
     // fused V,V / H,H walks halve the traffic of those passes but need two rings per warp (4 warps per SM); measured
     // 23.7 ms vs 21.0 ms per 1080p x 256 frame, so they are opt-in (SMT_AGG_FUSE=1)
     static const bool fuse_pairs = getenv("SMT_AGG_FUSE") != nullptr;
+    static const bool fuse_vertical_only = getenv("SMT_AGG_FUSE_V") != nullptr;
     // default: the streaming one-warp-per-line kernel (cross_agg_seq.cu); SMT_AGG_KERNEL=tile selects the tiled one
     static const bool use_tile = getenv("SMT_AGG_KERNEL") != nullptr && std::string(getenv("SMT_AGG_KERNEL")) == "tile";
     if (!use_tile) {
@@ -272,7 +273,7 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
         for (size_t k = 0; k < passes.size();) {
             // a dividing pass followed by a non-dividing pass in the same direction (V,V / H,H) runs as one fused walk
             const bool pair = fuse_pairs && k + 1 < passes.size() && passes[k + 1].horiz == passes[k].horiz && passes[k].sup &&
-                              !passes[k + 1].sup;
+                              !passes[k + 1].sup && (!fuse_vertical_only || !passes[k].horiz);
             // the last pass feeds only a winner-take-all: reduce in the kernel, never write the volume
             if (wta_disp && nonneg && k + 1 == passes.size() && passes[k].sup) {
                 SMT_TRY(k_agg_seq_pass_wta(ctx, cur, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, b_sum, wta_disp));
@@ -280,7 +281,10 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
                 return SMT_OK;
             }
             if (pair) {
-                SMT_TRY(k_agg_seq_pair(ctx, cur, oth, arms8, passes[k].sup, H, W, D, passes[k].horiz ? 1 : 0, nonneg, b_sum, b_plain));
+                if (passes[k].horiz)
+                    SMT_TRY(k_agg_seq_pair(ctx, cur, oth, arms8, passes[k].sup, H, W, D, 1, nonneg, b_sum, b_plain, 0));
+                else
+                    SMT_TRY(k_agg_seq_pair(ctx, cur, oth, armsT.as<uint8_t>(), sup0T.as<uint16_t>(), H, W, D, 0, nonneg, b_sum, b_plain, 1));
                 k += 2;
             } else {
                 if (passes[k].horiz)

@@ -729,6 +729,202 @@ static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const
     return SMT_OK;
 }
 
+// ================================================================================================ fused pair, warp pair
+// Two passes along the same direction (A divides, B does not) by a PAIR of warps of one block: warp 0 runs pass A on a
+// (line, 32-disparity) task exactly like agg_seq_kernel but puts its outputs into a double-buffered 2 x 3 KB queue in
+// shared memory instead of the volume; warp 1 runs pass B with the queue as its input and writes the volume.  One
+// __syncthreads per chunk hands a buffer over.  B's prefix positions are A's output positions, chunk o of B covers
+// positions 24o-35 .. 24o-12 (what A emitted in its chunk o), so E_B[q] lives at ring slot (q+35) mod 72 and every ring
+// store of B has the same compile-time offset as A's; B emits i = 24o-70+k.  Per pair: two rings + queue = 42 KB, five
+// pairs per SM.
+constexpr int SEQP_LOOKB = 2 * SEQ_LOOK;  // 70
+struct PrefetchedP {
+    unsigned armw;
+    int cnt;
+};
+
+// ROLE 1 = producer (pass A), 2 = consumer (pass B)
+template <bool NONNEG, int ROLE, bool EDGE>
+__device__ __forceinline__ void seqp_chunk(pair2& acc, PrefetchedP& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len,
+                                           bool act, const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
+                                           long long mbase, long long mstride, int horiz, const unsigned* __restrict__ arms,
+                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, float* queue,
+                                           int lane, int zero) {
+    constexpr int LOOK = ROLE == 1 ? SEQ_LOOK : SEQP_LOOKB;      // output position = tb - LOOK + k
+    constexpr int SHIFT = ROLE == 1 ? 0 : SEQ_LOOK;              // E[q] lives at slot (q + SHIFT) mod R
+    const long long step_b = step * 4;
+    {
+        const int j = tb - LOOK + lane;
+        Desc ds{0u, 0u, 1.f, 1.f};
+        if (lane < SEQ_CH && (!EDGE || (j >= 0 && j < len))) {
+            const unsigned aw = horiz ? (pre.armw & 0xffffu) : (pre.armw >> 16);
+            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
+            ds.offa = (unsigned)((max(j - lo, 0) + SHIFT) % SEQ_R) * 256u;
+            ds.offb = (unsigned)((min(j + hi + 1, len) + SHIFT) % SEQ_R) * 256u;
+            if (ROLE == 1) {
+                ds.cnt = (float)pre.cnt;
+                ds.rcp = __frcp_rn(ds.cnt);
+            }
+        }
+        __syncwarp();
+        if (lane < SEQ_CH) desc[lane] = ds;
+        __syncwarp();
+    }
+    unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;
+    char* dp = reinterpret_cast<char*>(dst_first);  // ROLE 2: output position tb - 70
+    if (ROLE == 2) {
+#pragma unroll
+        for (int k = 0; k < SEQ_CH; ++k) vuse[k] = queue[k * 32 + lane];
+    }
+    *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);
+    acc = pre_add<NONNEG>(acc, vuse[0]);
+    const int dep = __float_as_int(acc.a) & zero;
+    {
+        if (ROLE == 1) {
+            const char* p = reinterpret_cast<const char*>(src_next + dep);
+#pragma unroll
+            for (int k = 0; k < SEQ_CH; ++k) {
+                if (EDGE)
+                    vload[k] = (tb + SEQ_CH + k < len && act) ? __ldcs(reinterpret_cast<const float*>(p)) : 0.f;
+                else
+                    vload[k] = __ldcs(reinterpret_cast<const float*>(p));
+                p += step_b;
+            }
+#if SMT_SEQ_L2PF > 0
+            const int q = tb + (1 + SMT_SEQ_L2PF) * SEQ_CH + lane;
+            if (lane < SEQ_CH && q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
+#endif
+        }
+        const int jn = tb - LOOK + lane + SEQ_CH;
+        pre.armw = 0u;
+        pre.cnt = 1;
+        if (lane < SEQ_CH && jn >= 0 && jn < len) {
+            const long long pix = mbase + mstride * jn + dep;
+            pre.armw = __ldg(arms + pix);
+            if (ROLE == 1) pre.cnt = (int)__ldg(sup + pix);
+        }
+    }
+    {
+        Desc dsc[SEQ_CH];
+        float2 ea[SEQ_CH], eb[SEQ_CH];
+#pragma unroll
+        for (int u = 0; u < SEQ_DLAG; ++u) dsc[u] = desc[u];
+#pragma unroll
+        for (int k = 0; k < SEQ_CH + SEQ_RLAG; ++k) {
+            if (k < SEQ_CH) {
+                if (k > 0) {
+                    *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);
+                    acc = pre_add<NONNEG>(acc, vuse[k]);
+                }
+                ea[k] = *reinterpret_cast<const float2*>(ring_col + dsc[k].offa);
+                eb[k] = *reinterpret_cast<const float2*>(ring_col + dsc[k].offb);
+                if (k + SEQ_DLAG < SEQ_CH) dsc[k + SEQ_DLAG] = desc[k + SEQ_DLAG];
+            }
+            if (k >= SEQ_RLAG) {
+                const int kk = k - SEQ_RLAG;
+                const bool inside = !EDGE || (tb - LOOK + kk >= 0 && tb - LOOK + kk < len);  // warp-uniform
+                float r = __fadd_rn(__fsub_rn(eb[kk].x, ea[kk].x), __fsub_rn(eb[kk].y, ea[kk].y));
+                if (ROLE == 1) {
+                    r = div_by_count(r, dsc[kk].cnt, dsc[kk].rcp);
+                    queue[kk * 32 + lane] = (inside && (!EDGE || act)) ? r : 0.f;  // positions outside the line feed zeros into pass B
+                } else {
+                    if (inside && (!EDGE || act)) __stcs(reinterpret_cast<float*>(dp), r);
+                    dp += step_b;
+                }
+            }
+        }
+    }
+}
+
+constexpr int SEQP_SMEM = 2 * SEQ_R * 256 + 2 * SEQ_CH * 128;  // two rings + two queue buffers
+
+template <bool NONNEG>
+__global__ void __launch_bounds__(64, 5) agg_seqp_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a, int H, int W,
+                                                         int D, int horiz, float bias_a, float bias_b, int zero, int tmaps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Desc s_desc_all[2][SEQ_CH];
+    const int lane = threadIdx.x & 31, role = 1 + (threadIdx.x >> 5);  // warp 0: pass A, warp 1: pass B
+    unsigned char* ring_col = smem_raw + (size_t)(role - 1) * SEQ_R * 256 + lane * 8;
+    float* queue = reinterpret_cast<float*>(smem_raw + 2 * SEQ_R * 256);  // [2][SEQ_CH][32]
+    Desc* s_desc = s_desc_all[role - 1];
+    const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
+    const int nchunk = (D + 31) >> 5;
+    const long long wg = blockIdx.x;
+    const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
+    const int len = horiz ? W : H;
+    const int d = chunk * 32 + lane;
+    const bool act = d < D;
+    const bool full = chunk * 32 + 32 <= D;
+    const long long pstride = horiz ? 1 : (long long)W;
+    const long long pbase = horiz ? (long long)line * W : (long long)line;
+    const long long step = pstride * D;
+    const float* src = in + pbase * D + (act ? d : 0);
+    float* dst = out + pbase * D + (act ? d : 0);
+    const long long mstride = (!horiz && tmaps) ? 1 : pstride;
+    const long long mbase = (!horiz && tmaps) ? (long long)line * H : pbase;
+
+    pair2 acc{NONNEG ? (role == 1 ? bias_a : bias_b) : 0.f, 0.f};
+    float va[SEQ_CH], vb[SEQ_CH];
+#pragma unroll
+    for (int k = 0; k < SEQ_CH; ++k) {
+        va[k] = (role == 1 && k < len && act) ? __ldcs(src + step * k) : 0.f;
+        vb[k] = 0.f;
+    }
+    PrefetchedP pre{0u, 1};
+    const int nouter = (len + SEQP_LOOKB + SEQ_CH - 1) / SEQ_CH;  // chunks of pass B; pass A keeps running (zeros) to feed them
+    // iteration it: A does its chunk `it` into queue buffer it&1, B does its chunk `it-1` from the buffer A filled last time
+#define SMT_SEQP_STEP(USE, LOAD)                                                                                                        \
+    if (it <= nouter) {                                                                                                                 \
+        if (role == 1) {                                                                                                                \
+            if (it < nouter) {                                                                                                          \
+                const int tb = it * SEQ_CH;                                                                                             \
+                const float* src_next = src + step * (tb + SEQ_CH);                                                                     \
+                float* qb = queue + (it & 1) * SEQ_CH * 32;                                                                             \
+                if (full && tb - SEQ_LOOK >= 0 && tb + 2 * SEQ_CH <= len)                                                               \
+                    seqp_chunk<NONNEG, 1, false>(acc, pre, USE, LOAD, tb, len, act, src_next, nullptr, step, mbase, mstride, horiz, arms, \
+                                                 sup_a, ring_col, s_desc, qb, lane, zero);                                              \
+                else                                                                                                                    \
+                    seqp_chunk<NONNEG, 1, true>(acc, pre, USE, LOAD, tb, len, act, src_next, nullptr, step, mbase, mstride, horiz, arms,  \
+                                                sup_a, ring_col, s_desc, qb, lane, zero);                                               \
+            }                                                                                                                           \
+        } else if (it >= 1) {                                                                                                           \
+            const int tb = (it - 1) * SEQ_CH;                                                                                           \
+            float* dst_first = dst + step * (tb - SEQP_LOOKB);                                                                          \
+            float* qb = queue + ((it - 1) & 1) * SEQ_CH * 32;                                                                           \
+            if (full && tb - SEQP_LOOKB >= 0 && tb - SEQP_LOOKB + SEQ_CH <= len)                                                        \
+                seqp_chunk<NONNEG, 2, false>(acc, pre, USE, LOAD, tb, len, act, nullptr, dst_first, step, mbase, mstride, horiz, arms,    \
+                                             sup_a, ring_col, s_desc, qb, lane, zero);                                                  \
+            else                                                                                                                        \
+                seqp_chunk<NONNEG, 2, true>(acc, pre, USE, LOAD, tb, len, act, nullptr, dst_first, step, mbase, mstride, horiz, arms,     \
+                                            sup_a, ring_col, s_desc, qb, lane, zero);                                                   \
+        }                                                                                                                               \
+        __syncthreads();                                                                                                                \
+        ++it;                                                                                                                           \
+    }
+    for (int it = 0; it <= nouter;) {
+        SMT_SEQP_STEP(va, vb)
+        SMT_SEQP_STEP(vb, va)
+    }
+#undef SMT_SEQP_STEP
+}
+
+template <bool NONNEG>
+static smt_status_t launch_seqp(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
+                                int horiz, float bias_a, float bias_b, int tmaps) {
+    static bool attr_set_dev[64] = {};
+    bool& attr_set = attr_set_dev[ctx->device & 63];
+    if (!attr_set) {
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqp_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQP_SMEM));
+        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqp_kernel<NONNEG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    const long long ntask = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    SMT_LAUNCH(ctx, (agg_seqp_kernel<NONNEG>), (unsigned)ntask, 64, SEQP_SMEM, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b, 0, tmaps);
+    return SMT_OK;
+}
+
 template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
                                int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0) {
@@ -831,14 +1027,18 @@ smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* ar
 
 // pass A (divides by sup_a) followed by pass B (no division) along the same direction, in one walk
 smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
-                            int horiz, bool nonneg, float bias_a, float bias_b) {
+                            int horiz, bool nonneg, float bias_a, float bias_b, int tmaps) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
-    static const bool two_rings = getenv("SMT_AGG_FUSE") != nullptr && std::string(getenv("SMT_AGG_FUSE")) == "rings";
-    if (!two_rings)
+    // SMT_AGG_FUSE: "pair" (or 1) = producer / consumer warp pair, "hw" = half-warp roles, "rings" = two rings per lane
+    static const std::string how = getenv("SMT_AGG_FUSE") ? getenv("SMT_AGG_FUSE") : "";
+    if (how == "rings" && !tmaps)
+        return nonneg ? launch_seq2<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
+                      : launch_seq2<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
+    if (how == "hw" && !tmaps)
         return nonneg ? launch_seqh<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
                       : launch_seqh<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
-    return nonneg ? launch_seq2<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
-                  : launch_seq2<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
+    return nonneg ? launch_seqp<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b, tmaps)
+                  : launch_seqp<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b, tmaps);
 }
 
 // ---------------------------------------------------------------------------------------------- per-sweep C ABI (row bands)
