@@ -323,6 +323,19 @@ def gpu_arm(args, H, W, D):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if world == 1 and mode == SUM_FAST:
+        # the bit-exact aggregation mode (SMT_SUM_REFERENCE_ORDER) beside the benchmarked one, one timed step
+        pex = eng.default_params(H, W, D)
+        pex.sum_mode = SUM_REFERENCE_ORDER
+
+        def step_exact():
+            for fr in dev_frames:
+                eng.pipeline(fr["bgr_left"], fr["bgr_right"], D, fr["gray_left"], fr["gray_right"], params=pex)
+
+        step_exact()
+        ms_ex = timed(step_exact, 1)
+        line["reference_order_mode"] = {"value": aggregate_fps(world, B, 1, ms_ex), "unit": "frames/s", "ms_per_frame": ms_ex / B,
+                                        "note": "same pipeline with the bit-exact aggregation (taps added in the reference's order)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         workers = min(host_cores(), 32)
         rows, cols = cpu_sample_shape(H, W, D, 15.0)

@@ -171,6 +171,40 @@ __global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __rest
     out[cell] = acc;
 }
 
+// the same sums, four disparities per thread (D % 4 == 0, 16-byte aligned volumes): a quarter of the load instructions
+template <bool HORIZ>
+__global__ void __launch_bounds__(256) agg_pass_exact4_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                              const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
+                                                              int H, int W, int D4) {
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ncell = (size_t)H * W * D4;
+    if (cell >= ncell) return;
+    const size_t pix = cell / D4;
+    const int d4 = (int)(cell - pix * D4);
+    const uchar4 a = arms[pix];
+    const int lo = HORIZ ? -(int)a.x : -(int)a.z;
+    const int hi = HORIZ ? (int)a.y : (int)a.w;
+    const long long step = HORIZ ? (long long)D4 : (long long)W * D4;
+    const float4* p = in + (long long)pix * D4 + d4 + lo * step;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = lo; t <= hi; ++t) {
+        const float4 v = *p;
+        acc.x = __fadd_rn(acc.x, v.x);
+        acc.y = __fadd_rn(acc.y, v.y);
+        acc.z = __fadd_rn(acc.z, v.z);
+        acc.w = __fadd_rn(acc.w, v.w);
+        p += step;
+    }
+    if (sup) {
+        const float c = (float)(int)sup[pix];
+        acc.x = __fdiv_rn(acc.x, c);
+        acc.y = __fdiv_rn(acc.y, c);
+        acc.z = __fdiv_rn(acc.z, c);
+        acc.w = __fdiv_rn(acc.w, c);
+    }
+    out[cell] = acc;
+}
+
 // ---------------------------------------------------------------------------------------------- fast line passes
 // (implemented in cross_agg_fast.cu)
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
@@ -184,17 +218,30 @@ smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     const size_t ncell = (size_t)H * W * D;
     const unsigned grid = cdiv((long long)ncell, 256);
+    const bool vec4 = D % 4 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 15) == 0;
+    const unsigned grid4 = cdiv((long long)(ncell / 4), 256);
+    auto pass = [&](bool horiz, const float* src, float* dst, const uint16_t* s) -> smt_status_t {
+        if (vec4) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            if (horiz)
+                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<true>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+            else
+                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+        } else {
+            if (horiz)
+                SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, src, dst, arms, s, H, W, D);
+            else
+                SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, src, dst, arms, s, H, W, D);
+        }
+        return SMT_OK;
+    };
     bool hfirst = true;
     float* cur = vol;
     float* oth = tmp;
     for (int k = 0; k < iters; ++k) {
-        if (hfirst) {
-            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, cur, oth, arms, (const uint16_t*)nullptr, H, W, D);
-            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, oth, cur, arms, sup0, H, W, D);
-        } else {
-            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, cur, oth, arms, (const uint16_t*)nullptr, H, W, D);
-            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, oth, cur, arms, sup1, H, W, D);
-        }
+        SMT_TRY(pass(hfirst, cur, oth, nullptr));
+        SMT_TRY(pass(!hfirst, oth, cur, hfirst ? sup0 : sup1));
         hfirst = !hfirst;
     }
     *result = cur;  // every iteration ends back in `vol`
