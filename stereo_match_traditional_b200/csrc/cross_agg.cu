@@ -12,6 +12,8 @@
 //   SMT_SUM_REFERENCE_ORDER  each cell adds its taps sequentially in the reference's order (t ascending, starting
 //                            from 0.0f, :358-383) -> bit-identical to the reference.
 //   SMT_SUM_FAST             see agg_line_kernel below.
+#include <cstdlib>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------- arms
@@ -205,6 +207,73 @@ __global__ void __launch_bounds__(256) agg_pass_exact4_kernel(const float4* __re
     out[cell] = acc;
 }
 
+// Four disparities AND four consecutive positions of the line per thread: the windows of neighbouring positions overlap
+// almost completely, so each tap row is loaded once for the four outputs and added (in ascending tap order, exactly the
+// reference's order for every output) to the ones whose window contains it.  A quarter of the L1 traffic again.
+template <bool HORIZ>
+__global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                               const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
+                                                               int H, int W, int D4) {
+    const int len = HORIZ ? W : H, nlines = HORIZ ? H : W;
+    const int ngrp = (len + 3) >> 2;
+    const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= (size_t)nlines * ngrp * D4) return;
+    const int d4 = (int)(item % D4);
+    const size_t lg = item / D4;
+    const int grp = (int)(lg % ngrp), line = (int)(lg / ngrp);
+    const int p0 = grp * 4;
+    const long long pstride = HORIZ ? 1 : (long long)W;                       // pixel stride along the line
+    const long long pbase = HORIZ ? (long long)line * W : (long long)line;   // pixel of position 0
+    int s[4], e[4];
+    int tmin = len, tmax = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pos = p0 + i;
+        s[i] = 1;
+        e[i] = 0;  // empty window for positions beyond the line
+        if (pos < len) {
+            const uchar4 a = arms[pbase + pstride * pos];
+            s[i] = pos - (HORIZ ? (int)a.x : (int)a.z);
+            e[i] = pos + (HORIZ ? (int)a.y : (int)a.w);
+            tmin = min(tmin, s[i]);
+            tmax = max(tmax, e[i]);
+        }
+    }
+    float4 acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* p = in + (pbase + pstride * tmin) * D4 + d4;
+    const long long step = pstride * D4;
+    for (int t = tmin; t <= tmax; ++t) {
+        const float4 v = *p;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (t >= s[i] && t <= e[i]) {
+                acc[i].x = __fadd_rn(acc[i].x, v.x);
+                acc[i].y = __fadd_rn(acc[i].y, v.y);
+                acc[i].z = __fadd_rn(acc[i].z, v.z);
+                acc[i].w = __fadd_rn(acc[i].w, v.w);
+            }
+        p += step;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pos = p0 + i;
+        if (pos < len) {
+            const long long pix = pbase + pstride * pos;
+            float4 r = acc[i];
+            if (sup) {
+                const float c = (float)(int)sup[pix];
+                r.x = __fdiv_rn(r.x, c);
+                r.y = __fdiv_rn(r.y, c);
+                r.z = __fdiv_rn(r.z, c);
+                r.w = __fdiv_rn(r.w, c);
+            }
+            out[pix * D4 + d4] = r;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- fast line passes
 // (implemented in cross_agg_fast.cu)
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
@@ -224,10 +293,19 @@ smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8
         if (vec4) {
             const float4* s4 = reinterpret_cast<const float4*>(src);
             float4* d4 = reinterpret_cast<float4*>(dst);
-            if (horiz)
-                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<true>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
-            else
-                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+            static const bool one_pos = getenv("SMT_EXACT_1POS") != nullptr;  // the four-disparity, one-position kernel
+            if (one_pos) {
+                if (horiz)
+                    SMT_LAUNCH(ctx, agg_pass_exact4_kernel<true>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+                else
+                    SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+            } else {
+                const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + 3) / 4) * (D / 4);
+                if (horiz)
+                    SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
+                else
+                    SMT_LAUNCH(ctx, agg_pass_exact44_kernel<false>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
+            }
         } else {
             if (horiz)
                 SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, src, dst, arms, s, H, W, D);
