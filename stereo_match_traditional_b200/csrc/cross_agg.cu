@@ -210,24 +210,28 @@ __global__ void __launch_bounds__(256) agg_pass_exact4_kernel(const float4* __re
 // Four disparities AND four consecutive positions of the line per thread: the windows of neighbouring positions overlap
 // almost completely, so each tap row is loaded once for the four outputs and added (in ascending tap order, exactly the
 // reference's order for every output) to the ones whose window contains it.  A quarter of the L1 traffic again.
+#ifndef SMT_EXACT_NP
+#define SMT_EXACT_NP 4
+#endif
+constexpr int EXACT_NP = SMT_EXACT_NP;  // consecutive positions per thread
 template <bool HORIZ>
 __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __restrict__ in, float4* __restrict__ out,
                                                                const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
                                                                int H, int W, int D4) {
     const int len = HORIZ ? W : H, nlines = HORIZ ? H : W;
-    const int ngrp = (len + 3) >> 2;
+    const int ngrp = (len + EXACT_NP - 1) / EXACT_NP;
     const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= (size_t)nlines * ngrp * D4) return;
     const int d4 = (int)(item % D4);
     const size_t lg = item / D4;
     const int grp = (int)(lg % ngrp), line = (int)(lg / ngrp);
-    const int p0 = grp * 4;
+    const int p0 = grp * EXACT_NP;
     const long long pstride = HORIZ ? 1 : (long long)W;                       // pixel stride along the line
     const long long pbase = HORIZ ? (long long)line * W : (long long)line;   // pixel of position 0
-    int s[4], e[4];
+    int s[EXACT_NP], e[EXACT_NP];
     int tmin = len, tmax = -1;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < EXACT_NP; ++i) {
         const int pos = p0 + i;
         s[i] = 1;
         e[i] = 0;  // empty window for positions beyond the line
@@ -239,15 +243,15 @@ __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __r
             tmax = max(tmax, e[i]);
         }
     }
-    float4 acc[4];
+    float4 acc[EXACT_NP];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < EXACT_NP; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* p = in + (pbase + pstride * tmin) * D4 + d4;
     const long long step = pstride * D4;
     for (int t = tmin; t <= tmax; ++t) {
         const float4 v = *p;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < EXACT_NP; ++i)
             if (t >= s[i] && t <= e[i]) {
                 acc[i].x = __fadd_rn(acc[i].x, v.x);
                 acc[i].y = __fadd_rn(acc[i].y, v.y);
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __r
         p += step;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < EXACT_NP; ++i) {
         const int pos = p0 + i;
         if (pos < len) {
             const long long pix = pbase + pstride * pos;
@@ -300,7 +304,7 @@ smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8
                 else
                     SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
             } else {
-                const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + 3) / 4) * (D / 4);
+                const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + EXACT_NP - 1) / EXACT_NP) * (D / 4);
                 if (horiz)
                     SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
                 else
