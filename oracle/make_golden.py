@@ -36,6 +36,13 @@ ADCENSUS_CASES = [
     ("adc_scene_48x200x24", 48, 200, 24, "scene", 7, False),
     ("adc_scene_33x257x40", 33, 257, 40, "scene", 8, False),
     ("adc_const_30x70x32", 30, 70, 32, "constant", 12, False),
+    # degenerate shapes: smaller than the census window / one arm, D = 1, D > W, one row, one column
+    ("adc_noise_9x9x1", 9, 9, 1, "noise", 118, False),
+    ("adc_noise_3x40x6", 3, 40, 6, "noise", 143, False),
+    ("adc_noise_20x8x12", 20, 8, 12, "noise", 128, False),
+    ("adc_noise_1x50x4", 1, 50, 4, "noise", 151, False),
+    ("adc_noise_50x1x1", 50, 1, 1, "noise", 151, False),
+    ("adc_noise_35x36x65", 35, 36, 65, "noise", 171, False),
 ]
 
 
