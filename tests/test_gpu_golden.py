@@ -67,3 +67,67 @@ def test_cuda_path_reproduces_golden_arrays(engine):
         for k in got:
             if k in z.files:
                 assert np.array_equal(np.asarray(got[k]), z[k], equal_nan=True), f"{f.stem}: {k}"
+
+
+# ---------------------------------------------------------------------------------------------- matchers, CrossArm, CBLSM
+from stereo_match_traditional_b200.synth import replicate_pad  # noqa: E402
+
+MAT_CASES = [k for k in DIGESTS if k.startswith("mat_")]
+CA_CASES = [k for k in DIGESTS if k.startswith("ca_")]
+
+
+@pytest.mark.parametrize("case", MAT_CASES)
+def test_matchers_against_reference_digests(engine, case):
+    """SAD is integer work (digests must match); NCC / ASW disparities are held to >= 99.9 % where the full golden arrays
+    are committed and must at least have the digest's shape elsewhere."""
+    meta = DIGESTS[case]
+    H, W, D = meta["shape"]
+    p = make_pair(H, W, D, meta["seed"], meta["kind"])
+    lp, rp = replicate_pad(p["gray_left"], 4), replicate_pad(p["gray_right"], 4)
+    disp, costs = engine.sad(lp, rp, D, 3, want_costs=True)
+    want = meta["outputs"]
+    assert digest(disp) == want["sad_left"]
+    assert digest(costs) == want["sad_costs_left"]
+    assert digest(engine.sad(lp, rp, D, 3, right_view=True)) == want["sad_right"]
+    ncc = engine.ncc(p["gray_left"], p["gray_right"], D, 4)
+    asw_l = engine.asw(lp, rp, D, 3, 50, 30, 40)
+    asw_r = np.ascontiguousarray(engine.asw(lp, rp, D, 3, 50, 30, 40, right_view=True)[:, : W - 3 - 2])
+    f = GOLDEN / f"{case}.npz"
+    if f.exists():
+        z = np.load(f)
+        assert (ncc == z["ncc_w4"]).mean() >= 0.999
+        assert (asw_l == z["asw_left"]).mean() >= 0.999
+        assert (asw_r == z["asw_right_defined"]).mean() >= 0.999
+        assert np.array_equal(engine.asw_crosscheck(z["asw_left"], np.zeros_like(z["asw_left"])), z["asw_crosscheck"])
+    else:
+        for got, key in ((ncc, "ncc_w4"), (asw_l, "asw_left"), (asw_r, "asw_right_defined")):
+            assert digest(got).split(":", 1)[1] == want[key].split(":", 1)[1], key   # dtype and shape
+
+
+@pytest.mark.parametrize("case", CA_CASES)
+def test_crossarm_cblsm_against_reference_digests(engine, case):
+    from stereo_match_traditional_b200.api import SUM_REFERENCE_ORDER
+
+    meta = DIGESTS[case]
+    H, W, D = meta["shape"]
+    p = make_pair(H, W, D, meta["seed"], meta["kind"])
+    want = meta["outputs"]
+    vol = np.random.default_rng(meta["seed"]).random((H, W, D), dtype=np.float32)
+    for tag, img in (("gray", p["gray_left"]), ("bgr", p["bgr_left"])):
+        a = engine.arms_gray(img, 30, 34, 17, variant=0)
+        for k in ("left", "right", "top", "bottom"):
+            assert digest(a[k]) == want[f"crossarm_{tag}_{k}"], (tag, k)
+        assert digest(np.array([a["tao_final"]], np.int32)) == want[f"crossarm_{tag}_tao"]
+        aggv = engine.aggregate_rect(vol, a["left"], a["right"], a["top"], a["bottom"], variant=0, mode=SUM_REFERENCE_ORDER)
+        assert digest(aggv) == want[f"crossarm_{tag}_aggv"], tag
+        c = engine.arms_gray(img, 25, 34, 17, variant=1)
+        for k in ("left", "right", "up", "down"):
+            assert digest(c[k]) == want[f"cblsm_{tag}_{k}"], (tag, k)
+    adL, adR = engine.ad_cost(p["gray_left"], p["gray_right"], D, 0), engine.ad_cost(p["gray_left"], p["gray_right"], D, 1)
+    assert digest(adL) == want["cblsm_adL"] and digest(adR) == want["cblsm_adR"]
+    arms = engine.arms_gray(p["gray_left"], 25, 34, 17, variant=1)
+    order = ("left", "right", "up", "down")
+    v1 = engine.aggregate_rect(adL, *[arms[k] for k in order], variant=2, mode=SUM_REFERENCE_ORDER)
+    v2 = engine.aggregate_rect(v1, *[arms[k] for k in order], variant=2, mode=SUM_REFERENCE_ORDER)
+    assert digest(v1) == want["cblsm_v5_1"] and digest(v2) == want["cblsm_v5_2"]
+    assert digest(engine.wta(v2)) == want["cblsm_wta"]
