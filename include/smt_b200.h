@@ -120,18 +120,20 @@ SMT_API smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const
                                          int32_t iters, smt_sum_mode_t mode, float* cost_out, uint8_t* arms_out,
                                          uint16_t* sup_hfirst, uint16_t* sup_vfirst, smt_memspace_t space);
 
-/* Row-band form of smt_aggregate_cross (SMT_SUM_FAST) for one very large frame split over several GPUs
+/* Row-band form of smt_aggregate_cross for one very large frame split over several GPUs
  * (BASELINE.json configs[4]): the 2*iters one-dimensional passes are exposed one by one so the host can refresh the
  * 34-row halos between them (a vertical pass reads 34 rows beyond the band; horizontal passes are row-local).
  * vol_in / vol_out: float32 [rows][cols][D] band buffers INCLUDING their halo rows; arms / sup_*: the same rows of the
  * FULL image's maps (smt_cross_arms on the whole image, then sliced).  Results in halo rows are unspecified.
+ * mode: SMT_SUM_REFERENCE_ORDER makes the bands bit-identical to the whole frame (and to the reference); SMT_SUM_FAST
+ * agrees with the whole-frame fast result to ~2e-7 (a band's vertical prefix starts at a different row).
  * Device memspace only.  smt_cross_sweep_info reports the direction (1 = along rows) and whether the pass divides. */
 SMT_API int32_t smt_cross_sweep_count(int32_t iters);
 SMT_API smt_status_t smt_cross_sweep_info(int32_t iters, int32_t sweep, int32_t* horizontal, int32_t* divides);
 SMT_API smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t sweep, const float* vol_in,
                                                float* vol_out, const uint8_t* arms, const uint16_t* sup_hfirst,
                                                const uint16_t* sup_vfirst, int32_t rows, int32_t cols, int32_t D,
-                                               float vmax, smt_memspace_t space);
+                                               float vmax, smt_sum_mode_t mode, smt_memspace_t space);
 
 /* ------------------------------------------------------------------------------------------------ CrossArm / CBLSM
  * smt_ad_cost replaces CBLSM's ComputeAD / ComputeADRight (CBLSM/CBLSM.h:327, :355) and AD_Census::ComputeAD[Right]

@@ -73,7 +73,7 @@ SIGNATURES = {
     "smt_aggregate_cross": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "smt_cross_sweep_count": (_i, [_i]),
     "smt_cross_sweep_info": (_i, [_i, _i, _i32p, _i32p]),
-    "smt_aggregate_cross_sweep": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i]),
+    "smt_aggregate_cross_sweep": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i]),
     "smt_ad_cost": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
     "smt_arms_gray": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i32p, _i]),
     "smt_aggregate_rect": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),

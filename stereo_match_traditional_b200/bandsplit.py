@@ -69,11 +69,12 @@ def exchange_halos(buf, band: Band, group=None):
 
 
 def aggregate_cross_band(engine, bgr_full, cost_band, band: Band, iters: int = 4, L1=34, L2=17, t1=20, t2=6, vmax=None, group=None,
-                         timings: dict | None = None):
+                         timings: dict | None = None, mode: int = 1):
     """CrossAggregator::Aggregate(iters) on this rank's band.
 
     bgr_full: uint8 [H, W, 3] CUDA tensor of the WHOLE image (arms need +-34 rows of it).
     cost_band: float32 [band.nrows, W, D] CUDA tensor, the initial cost of the buffered rows (owned + halo).
+    mode: 1 = SMT_SUM_FAST (default), 0 = SMT_SUM_REFERENCE_ORDER (bands bit-identical to the whole frame).
     Returns the aggregated cost of the OWNED rows, [r1-r0, W, D] (a view into one of two band buffers)."""
     import torch
 
@@ -106,7 +107,7 @@ def aggregate_cross_band(engine, bgr_full, cost_band, band: Band, iters: int = 4
             torch.cuda.current_stream().synchronize()       # halos landed before the engine's stream reads them
         engine._ck(lib.smt_aggregate_cross_sweep(h, iters, s, C.c_void_p(cur.data_ptr()), C.c_void_p(oth.data_ptr()),
                                                  C.c_void_p(arms.data_ptr()), C.c_void_p(sup0.data_ptr()),
-                                                 C.c_void_p(sup1.data_ptr()), band.nrows, W, D, float(vmax), 1))
+                                                 C.c_void_p(sup1.data_ptr()), band.nrows, W, D, float(vmax), int(mode), 1))
         cur, oth = oth, cur
     engine.sync()
     if timings is not None:

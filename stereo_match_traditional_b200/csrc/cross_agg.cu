@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __rest
     const size_t pix = cell / D;
     const int d = (int)(cell - pix * D);
     const uchar4 a = arms[pix];
-    const int lo = HORIZ ? -(int)a.x : -(int)a.z;
-    const int hi = HORIZ ? (int)a.y : (int)a.w;
+    // arms stop at the image border; the clamps only act on the halo rows of a row band, whose results are never used
+    const int pos = HORIZ ? (int)(pix % W) : (int)(pix / W), len = HORIZ ? W : H;
+    const int lo = -min(HORIZ ? (int)a.x : (int)a.z, pos);
+    const int hi = min(HORIZ ? (int)a.y : (int)a.w, len - 1 - pos);
     const long long step = HORIZ ? (long long)D : (long long)W * D;
     const float* p = in + (long long)pix * D + d + lo * step;
     float acc = 0.0f;
@@ -184,8 +186,9 @@ __global__ void __launch_bounds__(256) agg_pass_exact4_kernel(const float4* __re
     const size_t pix = cell / D4;
     const int d4 = (int)(cell - pix * D4);
     const uchar4 a = arms[pix];
-    const int lo = HORIZ ? -(int)a.x : -(int)a.z;
-    const int hi = HORIZ ? (int)a.y : (int)a.w;
+    const int pos = HORIZ ? (int)(pix % W) : (int)(pix / W), len = HORIZ ? W : H;
+    const int lo = -min(HORIZ ? (int)a.x : (int)a.z, pos);
+    const int hi = min(HORIZ ? (int)a.y : (int)a.w, len - 1 - pos);
     const long long step = HORIZ ? (long long)D4 : (long long)W * D4;
     const float4* p = in + (long long)pix * D4 + d4 + lo * step;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -237,8 +240,8 @@ __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __r
         e[i] = 0;  // empty window for positions beyond the line
         if (pos < len) {
             const uchar4 a = arms[pbase + pstride * pos];
-            s[i] = pos - (HORIZ ? (int)a.x : (int)a.z);
-            e[i] = pos + (HORIZ ? (int)a.y : (int)a.w);
+            s[i] = max(pos - (HORIZ ? (int)a.x : (int)a.z), 0);  // clamps: see agg_pass_exact_kernel
+            e[i] = min(pos + (HORIZ ? (int)a.y : (int)a.w), len - 1);
             tmin = min(tmin, s[i]);
             tmax = max(tmax, e[i]);
         }
@@ -283,40 +286,46 @@ __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __r
 smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
                                     const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result, float* wta_disp);
 
+// one reference-order pass (taps added sequentially in ascending order, starting from 0.0f)
+smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const uint8_t* arms8, const uint16_t* s, int H, int W, int D,
+                              int horiz) {
+    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    const size_t ncell = (size_t)H * W * D;
+    const unsigned grid = cdiv((long long)ncell, 256);
+    const bool vec4 = D % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const unsigned grid4 = cdiv((long long)(ncell / 4), 256);
+    if (vec4) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        static const bool one_pos = getenv("SMT_EXACT_1POS") != nullptr;  // the four-disparity, one-position kernel
+        if (one_pos) {
+            if (horiz)
+                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<true>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+            else
+                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
+        } else {
+            const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + EXACT_NP - 1) / EXACT_NP) * (D / 4);
+            if (horiz)
+                SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
+            else
+                SMT_LAUNCH(ctx, agg_pass_exact44_kernel<false>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
+        }
+    } else {
+        if (horiz)
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, src, dst, arms, s, H, W, D);
+        else
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, src, dst, arms, s, H, W, D);
+    }
+    return SMT_OK;
+}
+
 smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
                                const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result,
                                float* wta_disp) {
     if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, vmax, result, wta_disp);
     StageTimer t(ctx, ST_AGGREGATE);
-    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
-    const size_t ncell = (size_t)H * W * D;
-    const unsigned grid = cdiv((long long)ncell, 256);
-    const bool vec4 = D % 4 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 15) == 0;
-    const unsigned grid4 = cdiv((long long)(ncell / 4), 256);
     auto pass = [&](bool horiz, const float* src, float* dst, const uint16_t* s) -> smt_status_t {
-        if (vec4) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            static const bool one_pos = getenv("SMT_EXACT_1POS") != nullptr;  // the four-disparity, one-position kernel
-            if (one_pos) {
-                if (horiz)
-                    SMT_LAUNCH(ctx, agg_pass_exact4_kernel<true>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
-                else
-                    SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
-            } else {
-                const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + EXACT_NP - 1) / EXACT_NP) * (D / 4);
-                if (horiz)
-                    SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
-                else
-                    SMT_LAUNCH(ctx, agg_pass_exact44_kernel<false>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
-            }
-        } else {
-            if (horiz)
-                SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, src, dst, arms, s, H, W, D);
-            else
-                SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, src, dst, arms, s, H, W, D);
-        }
-        return SMT_OK;
+        return k_agg_exact_pass(ctx, src, dst, arms8, s, H, W, D, horiz ? 1 : 0);
     };
     bool hfirst = true;
     float* cur = vol;

@@ -961,6 +961,9 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
 
 }  // namespace
 
+smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const uint8_t* arms8, const uint16_t* s, int H, int W, int D,
+                              int horiz);  // cross_agg.cu
+
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
                             int horiz, bool nonneg, float bias, int tmaps) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
@@ -1058,7 +1061,7 @@ smt_status_t smt_cross_sweep_info(int32_t iters, int32_t sweep, int32_t* horizon
 
 smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t sweep, const float* vol_in, float* vol_out,
                                        const uint8_t* arms, const uint16_t* sup_hfirst, const uint16_t* sup_vfirst, int32_t rows,
-                                       int32_t cols, int32_t D, float vmax, smt_memspace_t space) {
+                                       int32_t cols, int32_t D, float vmax, smt_sum_mode_t mode, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, space == SMT_DEVICE, SMT_ERR_UNSUPPORTED, "smt_aggregate_cross_sweep: device memspace only");
     SMT_REQUIRE(ctx, vol_in && vol_out && vol_in != vol_out && arms && sup_hfirst && sup_vfirst && rows > 0 && cols > 0 && D > 0,
@@ -1070,6 +1073,7 @@ smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t swee
     StageTimer t(ctx, ST_AGGREGATE);
     const bool hfirst = (sweep / 2) % 2 == 0;
     const uint16_t* sup = divides ? (hfirst ? sup_hfirst : sup_vfirst) : nullptr;
+    if (mode == SMT_SUM_REFERENCE_ORDER) return k_agg_exact_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz);
     const bool nonneg = vmax > 0.f && vmax < 1e30f;
     float b = 1.f;
     while (nonneg && b < vmax) b *= 2.f;

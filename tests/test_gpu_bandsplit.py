@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from stereo_match_traditional_b200.api import SUM_FAST
+from stereo_match_traditional_b200.api import SUM_FAST, SUM_REFERENCE_ORDER
 from stereo_match_traditional_b200.bandsplit import HALO, aggregate_cross_band, make_band
 from stereo_match_traditional_b200.synth import make_pair
 
@@ -26,8 +26,9 @@ def test_single_band_equals_whole_frame(engine):
     assert torch.equal(out, full)
 
 
+@pytest.mark.parametrize("mode", [SUM_FAST, SUM_REFERENCE_ORDER], ids=["fast", "reference_order"])
 @pytest.mark.parametrize("H,W,D,world", [(150, 120, 40, 2), (300, 96, 33, 3), (200, 70, 64, 4)])
-def test_emulated_bands_match_whole_frame(engine, oracle, H, W, D, world):
+def test_emulated_bands_match_whole_frame(engine, oracle, H, W, D, world, mode):
     import torch
 
     p = make_pair(H, W, D, 52 + world, "scene")
@@ -35,7 +36,7 @@ def test_emulated_bands_match_whole_frame(engine, oracle, H, W, D, world):
     bgr = torch.as_tensor(p["bgr_left"], device=dev)
     gl, gr = torch.as_tensor(p["gray_left"], device=dev), torch.as_tensor(p["gray_right"], device=dev)
     cost = engine.ad_cost(gl, gr, D, 0)
-    full = engine.aggregate_cross(bgr, cost, mode=SUM_FAST)["cost"]
+    full = engine.aggregate_cross(bgr, cost, mode=mode)["cost"]
     maps = engine.cross_arms(bgr)
     bands = [make_band(r, world, H) for r in range(world)]
     cur = [cost[b.b0:b.b1].clone() for b in bands]
@@ -58,7 +59,7 @@ def test_emulated_bands_match_whole_frame(engine, oracle, H, W, D, world):
         for r, b in enumerate(bands):
             engine._ck(lib.smt_aggregate_cross_sweep(engine.h, 4, s, C.c_void_p(cur[r].data_ptr()), C.c_void_p(oth[r].data_ptr()),
                                                      C.c_void_p(sl[r]["arms"].data_ptr()), C.c_void_p(sl[r]["sup0"].data_ptr()),
-                                                     C.c_void_p(sl[r]["sup1"].data_ptr()), b.nrows, W, D, 255.0, 1))
+                                                     C.c_void_p(sl[r]["sup1"].data_ptr()), b.nrows, W, D, 255.0, int(mode), 1))
         cur, oth = oth, cur
     engine.sync()
     got = torch.cat([cur[r][b.top:b.top + b.r1 - b.r0] for r, b in enumerate(bands)], 0)
@@ -66,10 +67,13 @@ def test_emulated_bands_match_whole_frame(engine, oracle, H, W, D, world):
     same = float((got == full).float().mean())
     rel = ((got - full).abs() / full.abs().clamp_min(1e-30))
     rel[got == full] = 0
-    assert same >= 0.97 and float(rel.max()) <= 1e-6, (same, float(rel.max()))
+    if mode == SUM_REFERENCE_ORDER:
+        assert torch.equal(got, full)        # band split == single GPU, bit for bit (test pyramid level 4)
+    else:
+        assert same >= 0.97 and float(rel.max()) <= 1e-6, (same, float(rel.max()))
     # and the whole thing is the reference's CrossAggregator within the usual tolerance
     ref = oracle.cross_aggregate(p["bgr_left"], p["bgr_right"], cost.cpu().numpy())["cost"]
     g = got.cpu().numpy()
     r = np.abs(g - ref) / np.maximum(np.abs(ref), 1e-30)
     r[g == ref] = 0
-    assert r.max() <= 1e-5
+    assert r.max() <= (0.0 if mode == SUM_REFERENCE_ORDER else 1e-5)
