@@ -126,7 +126,10 @@ SMT_API smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const
  * vol_in / vol_out: float32 [rows][cols][D] band buffers INCLUDING their halo rows; arms / sup_*: the same rows of the
  * FULL image's maps (smt_cross_arms on the whole image, then sliced).  Results in halo rows are unspecified.
  * mode: SMT_SUM_REFERENCE_ORDER makes the bands bit-identical to the whole frame (and to the reference); SMT_SUM_FAST
- * agrees with the whole-frame fast result to ~2e-7 (a band's vertical prefix starts at a different row).
+ * keeps every window sum exact up to one rounding, so bands agree with the whole frame to ~1e-6.
+ * SMT_SUM_FAST supports arms <= 34 (the reference's cross_L1 default, adcensus_types.h:69): sweep 0 scans the arm map
+ * and returns SMT_ERR_UNSUPPORTED when it holds a longer arm.  Sweeps of one aggregation must be issued in order,
+ * starting with sweep 0, on the same context.
  * Device memspace only.  smt_cross_sweep_info reports the direction (1 = along rows) and whether the pass divides. */
 SMT_API int32_t smt_cross_sweep_count(int32_t iters);
 SMT_API smt_status_t smt_cross_sweep_info(int32_t iters, int32_t sweep, int32_t* horizontal, int32_t* divides);
@@ -134,6 +137,16 @@ SMT_API smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int3
                                                float* vol_out, const uint8_t* arms, const uint16_t* sup_hfirst,
                                                const uint16_t* sup_vfirst, int32_t rows, int32_t cols, int32_t D,
                                                float vmax, smt_sum_mode_t mode, smt_memspace_t space);
+
+/* SMT_SUM_FAST evaluates window sums as differences of 32-bit wrap-around fixed-point prefixes (quantum = 2^-25 of the
+ * power of two above the largest cost).  That is accurate to 2^-20 per pass as long as every non-zero value entering a
+ * window is at least 2^19 quanta; lines that hold a smaller value are redone on compensated float32-pair prefixes, and
+ * when more than a quarter of a sweep's lines ask for it the rest of the aggregation runs on float pairs altogether.
+ * Both routes meet the 1e-5 bound of BASELINE.json; neither exists in the reference, which adds taps one by one
+ * (CBLSM/cross_aggregator.cpp:353-389).  This reports what the context's LAST fast aggregation did: the number of
+ * (line, 32-disparity chunk) tasks redone on float pairs (0 = pure fixed point), or -1 = float pairs took over.
+ * Synchronises the stream. */
+SMT_API smt_status_t smt_aggregate_fast_status(smt_ctx* ctx, int32_t* redone_tasks);
 
 /* ------------------------------------------------------------------------------------------------ CrossArm / CBLSM
  * smt_ad_cost replaces CBLSM's ComputeAD / ComputeADRight (CBLSM/CBLSM.h:327, :355) and AD_Census::ComputeAD[Right]
@@ -215,22 +228,26 @@ SMT_API smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32
  * costs (optional): float32 [..][..][D], the per-disparity SAD vector incl. the copy-previous rule (:125-129).
  *
  * smt_ncc replaces NCC_algorithem with ComputeCost and WinTakeAll (NCC/NCC.h:69, :15, :53): unpadded grey images
- * [rows][cols]; disp int32 [rows][cols], 0 outside the interior.
+ * [rows][cols]; disp int32 [rows][cols], 0 outside the interior.  costs (optional): float64 [rows][cols][D], the value
+ * ComputeCost returns per disparity (double in the reference, :15-49): 255 where the window leaves the image (:88), NaN for
+ * a zero-variance window, 0 at border pixels (which the reference never visits).
  *
  * smt_asw replaces AdaptiveSupportWeight / AdaptiveSupportWeightRight with getGausssianMask, getColorMask,
  * bilateralfiterWight, WinTakeAll (ASW/ASW.h:329, :382, :16, :41, :210, :193): replicate-padded grey images, pad =
  * win_size+1 (ASWeight.cpp:54-55); disp float32 [rows_padded-2*pad][cols_padded-2*pad].  In the right view the last
  * win_size+2 output columns are undefined in the reference (it reads costVolume[-1], ASW.h:401,:424); they are 0 here.
+ * costs (optional): float32 [..][..][D], the reference's costVolume row of each pixel (ASW.h:358-371, float of the double
+ * quotient) incl. the copy-previous rule for disparities whose window leaves the image.
  * smt_asw_crosscheck replaces CrossCheckDiaparity (ASW.h:108): out uint8 [rows][cols].
  */
 SMT_API smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded,
                              int32_t cols_padded, int32_t D, int32_t winsize, int32_t right_view, int32_t* disp,
                              float* costs, smt_memspace_t space);
 SMT_API smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols,
-                             int32_t win_size, int32_t D, int32_t* disp, smt_memspace_t space);
+                             int32_t win_size, int32_t D, int32_t* disp, double* costs, smt_memspace_t space);
 SMT_API smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded,
                              int32_t cols_padded, int32_t win_size, int32_t D, double space_sigma, double color_sigma,
-                             int32_t T, int32_t right_view, float* disp, smt_memspace_t space);
+                             int32_t T, int32_t right_view, float* disp, float* costs, smt_memspace_t space);
 SMT_API smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, const float* disp_right, int32_t rows,
                                         int32_t cols, uint8_t* out, smt_memspace_t space);
 

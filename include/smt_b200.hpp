@@ -44,6 +44,7 @@ struct ImageView {
 #endif
     /// dense copy when the view has row padding
     std::vector<uint8_t> dense() const {
+        if (!data || rows <= 0 || cols <= 0 || channels <= 0) throw Error(SMT_ERR_INVALID_ARG, "ImageView: null or empty image");
         const size_t row_bytes = (size_t)cols * channels;
         std::vector<uint8_t> out((size_t)rows * row_bytes);
         const size_t st = step ? step : row_bytes;
@@ -131,7 +132,9 @@ public:
         have_ = false;
     }
     // The four passes share one sticky threshold and must run in main.cpp:69-72 order; they are computed together
-    // on the first call and handed out one by one.
+    // on the first call with an image and handed out one by one.  A call with a DIFFERENT image (other buffer or
+    // geometry) recomputes all four from that image, continuing from the threshold the previous image left behind,
+    // like the reference's member _tao does (CrossArm.cpp:168-173); Initialize resets it.
     void ComputeLeftArmLength(const ImageView& Image) { arms(Image); }
     void ComputeRightArmLength(const ImageView& Image) { arms(Image); }
     void ComputeTopArmLength(const ImageView& Image) { arms(Image); }
@@ -146,7 +149,10 @@ public:
 
 private:
     void arms(const ImageView& im) {
-        if (have_) return;
+        if (have_ && im.data == key_.data && im.rows == key_.rows && im.cols == key_.cols && im.channels == key_.channels &&
+            im.step == key_.step)
+            return;
+        key_ = im;
         const std::vector<uint8_t> d = im.dense();
         int32_t tf = tao_;
         c_.check(smt_arms_gray(c_.get(), d.data(), im.channels, row_, col_, tao_, 34, 17, 0, leftLength.data(), rightLength.data(),
@@ -162,6 +168,7 @@ private:
     smt_sum_mode_t mode_;
     int row_ = 0, col_ = 0, tao_ = 0, D_ = 0;
     bool have_ = false;
+    ImageView key_;
 };
 
 // ------------------------------------------------------------------------------------------------ AD-CensusV1/ScanlineOptimizer.h:8-34
@@ -337,19 +344,19 @@ inline void GetPointDepthRight(int32_t* disparity, const ImageView& leftimg, con
 inline void NCC_algorithem(const ImageView& leftImage, const ImageView& rigthImage, const int width, const int height, int32_t* disp, int winSize,
                            int dispRange, Context& c = Context::Default()) {
     const std::vector<uint8_t> l = leftImage.dense(), r = rigthImage.dense();
-    c.check(smt_ncc(c.get(), l.data(), r.data(), height, width, winSize, dispRange, disp, SMT_HOST));
+    c.check(smt_ncc(c.get(), l.data(), r.data(), height, width, winSize, dispRange, disp, nullptr, SMT_HOST));
 }
 /// disp: float [rows-2*(winSize+1)][cols-2*(winSize+1)]; the Lab images and the masks of the reference signature are
 /// not needed (the Lab windows are never read, ASW.h:343; the masks are functions of the two sigmas).
 inline void AdaptiveSupportWeight(float* disp, const ImageView& leftGray, const ImageView& rightGray, const int winSize, int dispRange,
                                   double spaceSigma, double colorSigma, int T, Context& c = Context::Default()) {
     const std::vector<uint8_t> l = leftGray.dense(), r = rightGray.dense();
-    c.check(smt_asw(c.get(), l.data(), r.data(), leftGray.rows, leftGray.cols, winSize, dispRange, spaceSigma, colorSigma, T, 0, disp, SMT_HOST));
+    c.check(smt_asw(c.get(), l.data(), r.data(), leftGray.rows, leftGray.cols, winSize, dispRange, spaceSigma, colorSigma, T, 0, disp, nullptr, SMT_HOST));
 }
 inline void AdaptiveSupportWeightRight(float* disp, const ImageView& leftGray, const ImageView& rightGray, const int winSize, int dispRange,
                                        double spaceSigma, double colorSigma, int T, Context& c = Context::Default()) {
     const std::vector<uint8_t> l = leftGray.dense(), r = rightGray.dense();
-    c.check(smt_asw(c.get(), l.data(), r.data(), leftGray.rows, leftGray.cols, winSize, dispRange, spaceSigma, colorSigma, T, 1, disp, SMT_HOST));
+    c.check(smt_asw(c.get(), l.data(), r.data(), leftGray.rows, leftGray.cols, winSize, dispRange, spaceSigma, colorSigma, T, 1, disp, nullptr, SMT_HOST));
 }
 inline void CrossCheckDiaparity(const float* leftdisp, const float* rightdisp, uint8_t* lastdisp, int rows, int cols, Context& c = Context::Default()) {
     c.check(smt_asw_crosscheck(c.get(), leftdisp, rightdisp, rows, cols, lastdisp, SMT_HOST));

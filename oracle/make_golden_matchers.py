@@ -26,8 +26,10 @@ def matcher_outputs(o, H, W, D, kind, seed):
     out["sad_right"] = o.sad(lp, rp, D, 3, True)
     out["sad_costs_left"] = o.sad_costs_left(lp, rp, D, 3)
     out["ncc_w4"] = o.ncc(gl, gr, D, 4)
+    out["ncc_costs_w4"] = o.ncc_costs(gl, gr, D, 4)         # ComputeCost per (pixel, d), NaN on zero-variance windows
     la, ra = replicate_pad(gl, 4), replicate_pad(gr, 4)     # ASW winSize 3 -> pad 4
     out["asw_left"] = o.asw(la, ra, D, 3, 50, 30, 40)
+    out["asw_costs_left"] = o.asw_costs(la, ra, D, 3, 50, 30, 40)
     asw_r = o.asw(la, ra, D, 3, 50, 30, 40, True)
     out["asw_right_defined"] = np.ascontiguousarray(asw_r[:, : W - 3 - 2])   # ASW.h:401 reads costVolume[-1] beyond
     out["asw_crosscheck"] = o.asw_crosscheck(out["asw_left"], np.zeros_like(out["asw_left"]))

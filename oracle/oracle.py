@@ -303,6 +303,32 @@ class Oracle:
         self._fn("ncc")(_p(left, _u8p), _p(right, _u8p), H, W, win_size, D, _p(disp, _i32p))
         return disp
 
+    def ncc_costs(self, left, right, D, win_size=10, rows=None):
+        """ComputeCost per (pixel, d) for output rows [rows[0], rows[1]) -- float64 [n][W][D] (compiled reference only)."""
+        left = _c(left, np.uint8)
+        right = _c(right, np.uint8)
+        H, W = left.shape
+        i0, i1 = rows if rows is not None else (0, H)
+        out = np.zeros((i1 - i0, W, D), np.float64)
+        f = self._fn("ncc_costs")
+        f.restype = None
+        f(_p(left, _u8p), _p(right, _u8p), H, W, int(win_size), int(D), int(i0), int(i1), _p(out, _f64p))
+        return out
+
+    def asw_costs(self, left_padded, right_padded, D, win_size=11, space_sigma=50.0, color_sigma=30.0, T=40, rows=None):
+        """costVolume rows of AdaptiveSupportWeight for output rows [rows[0], rows[1]) -- float32 [n][Wo][D]."""
+        lp = _c(left_padded, np.uint8)
+        rp = _c(right_padded, np.uint8)
+        Hp, Wp = lp.shape
+        pad = win_size + 1
+        i0, i1 = rows if rows is not None else (0, Hp - 2 * pad)
+        out = np.zeros((i1 - i0, Wp - 2 * pad, D), np.float32)
+        f = self._fn("asw_costs")
+        f.restype = None
+        f(_p(lp, _u8p), _p(rp, _u8p), Hp, Wp, int(win_size), int(D), C.c_double(space_sigma), C.c_double(color_sigma), int(T),
+          int(i0), int(i1), _p(out, _f32p))
+        return out
+
     def ncc_cost(self, left, right, win_size, i, j, d):
         left = _c(left, np.uint8)
         right = _c(right, np.uint8)

@@ -734,6 +734,17 @@ void orc_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int 
     free(cost);
 }
 
+/* cost rows of output rows [i0, i1): NCC_algorithem's inner loop (:73-90); double [i1-i0][W][D] */
+void orc_ncc_costs(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int D, int i0, int i1, double* out) {
+    for (int i = i0; i < i1; ++i)
+        for (int j = 0; j < W; ++j) {
+            double* row = out + ((size_t)(i - i0) * W + j) * D;
+            const int interior = i >= winSize && i < H - winSize && j >= winSize && j < W - winSize;
+            for (int d = 0; d < D; ++d)
+                row[d] = !interior ? 0.0 : (j - winSize - d >= 0) ? orc_ncc_cost(L, R, H, W, winSize, i, j, d) : 255.0;
+        }
+}
+
 /* ------------------------------------------------------------------------------------------------ ASW (ASW/ASW.h) */
 void orc_asw_masks(int winSize, double spaceSigma, double colorSigma, double* space_out, double* color_out) {
     const int k = 2 * winSize + 3, c = (k - 1) / 2;
@@ -804,6 +815,26 @@ void orc_asw(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, 
         }
     free(space);
     free(cost);
+}
+
+/* costVolume rows of the left view for output rows [i0, i1) (:346-372); float [i1-i0][W][D] */
+void orc_asw_costs(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, int D, double spaceSigma, double colorSigma,
+                   int T, int i0, int i1, float* out) {
+    (void)Hp;
+    const int wins = winSize + 1, k = 2 * wins + 1, W = Wp - 2 * wins;
+    double* space = (double*)malloc((size_t)k * k * sizeof(double));
+    double color[256];
+    orc_asw_masks(winSize, spaceSigma, colorSigma, space, color);
+    for (int io = i0; io < i1; ++io)
+        for (int jo = 0; jo < W; ++jo) {
+            const int i = io + wins, j = jo + wins;
+            float* row = out + ((size_t)(io - i0) * W + jo) * D;
+            const uint8_t* a = Lp + (size_t)(i - wins) * Wp + (j - wins);
+            for (int d = 0; d < D; ++d)
+                row[d] = (j - wins - d >= 0) ? asw_cost(a, Rp + (size_t)(i - wins) * Wp + (j - wins - d), Wp, k, T, space, color)
+                                             : row[d - 1];
+        }
+    free(space);
 }
 
 /* CrossCheckDiaparity (:108-145) */

@@ -297,7 +297,60 @@ double ref_ncc_cost(const uint8_t* L, const uint8_t* R, int H, int W, int winSiz
     return c;
 }
 
+// NCC cost rows of output rows [i0, i1): the loop of NCC_algorithem (NCC.h:73-90) with the reference's ComputeCost doing
+// the arithmetic; out: double [i1-i0][W][D], 255 (`invalid`, :7) where the window leaves the image, 0 at border columns.
+void ref_ncc_costs(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int D, int i0, int i1, double* out) {
+    cv::Mat l = wrap_u8(L, H, W), r = wrap_u8(R, H, W);
+    for (int i = i0; i < i1; ++i)
+        for (int j = 0; j < W; ++j) {
+            double* row = out + ((size_t)(i - i0) * W + j) * D;
+            for (int d = 0; d < D; ++d) row[d] = 0.0;
+            if (i < winSize || i >= H - winSize || j < winSize || j >= W - winSize) continue;
+            cv::Mat wl = l(cv::Range(i - winSize, i + winSize + 1), cv::Range(j - winSize, j + winSize + 1));
+            for (int d = 0; d < D; ++d) {
+                if (j - winSize - d >= 0) {
+                    cv::Mat wr = r(cv::Range(i - winSize, i + winSize + 1), cv::Range(j - winSize - d, j + winSize - d + 1));
+                    rns_ncc::ComputeCost(wl, wr, row[d]);
+                } else {
+                    row[d] = 255.0;
+                }
+            }
+        }
+}
+
 // ---------------------------------------------------------------- ASW (ASW.h)
+// costVolume rows of output rows [i0, i1) of the left view: the loop of AdaptiveSupportWeight (ASW.h:336-374) with the
+// reference's bilateralfiterWight doing the arithmetic (the function itself keeps costVolume local and only returns the
+// winner).  out: float [i1-i0][Wo][D].
+void ref_asw_costs(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, int D, double spaceSigma, double colorSigma,
+                   int T, int i0, int i1, float* out) {
+    const int wins = winSize + 1, Wo = Wp - 2 * wins;
+    cv::Mat l = wrap_u8(Lp, Hp, Wp), r = wrap_u8(Rp, Hp, Wp);
+    cv::Mat space;
+    std::vector<double> color;
+    rns_asw::getGausssianMask(space, cv::Size(winSize * 2 + 3, winSize * 2 + 3), spaceSigma);
+    rns_asw::getColorMask(color, colorSigma);
+    for (int io = i0; io < i1; ++io)
+        for (int jo = 0; jo < Wo; ++jo) {
+            const int i = io + wins, j = jo + wins;
+            float* row = out + ((size_t)(io - i0) * Wo + jo) * D;
+            cv::Mat lw = l(cv::Range(i - wins, i + wins + 1), cv::Range(j - wins, j + wins + 1));
+            for (int d = 0; d < D; ++d) {
+                if (j - wins - d >= 0) {
+                    cv::Mat rw = r(cv::Range(i - wins, i + wins + 1), cv::Range(j - wins - d, j + wins - d + 1));
+                    cv::Mat error;
+                    cv::absdiff(lw, rw, error);
+                    for (int a = 0; a < error.rows; ++a)
+                        for (int b = 0; b < error.cols; ++b)
+                            if (error.at<uchar>(a, b) > T) error.at<uchar>(a, b) = T;
+                    row[d] = rns_asw::bilateralfiterWight(lw, rw, error, winSize, space, color);
+                } else {
+                    row[d] = row[d - 1];
+                }
+            }
+        }
+}
+
 // Lp/Rp: replicate-padded gray [Hp][Wp], pad = winSize+1 (ASWeight.cpp:54-55). disp: CV_32FC1 [H][W] zeroed by caller.
 void ref_asw(const uint8_t* Lp, const uint8_t* Rp, int Hp, int Wp, int winSize, int D, double spaceSigma,
              double colorSigma, int T, int right_view, float* disp) {

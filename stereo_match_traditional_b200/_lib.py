@@ -74,6 +74,7 @@ SIGNATURES = {
     "smt_cross_sweep_count": (_i, [_i]),
     "smt_cross_sweep_info": (_i, [_i, _i, _i32p, _i32p]),
     "smt_aggregate_cross_sweep": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i]),
+    "smt_aggregate_fast_status": (_i, [_vp, _i32p]),
     "smt_ad_cost": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
     "smt_arms_gray": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i32p, _i]),
     "smt_aggregate_rect": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
@@ -84,8 +85,8 @@ SIGNATURES = {
     "smt_median": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "smt_fill_the_hole": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i]),
     "smt_sad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i]),
-    "smt_ncc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
-    "smt_asw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _i, _i, _vp, _i]),
+    "smt_ncc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i]),
+    "smt_asw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _i, _i, _vp, _vp, _i]),
     "smt_asw_crosscheck": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
     "smt_bgr_to_gray": (_i, [_vp, _vp, _i, _i, _vp, _i]),
     "smt_replicate_pad": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),

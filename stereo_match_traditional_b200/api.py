@@ -259,6 +259,13 @@ class Engine:
             res.update(arms=arms, sup0=s0, sup1=s1)
         return res
 
+    def aggregate_fast_status(self) -> int:
+        """Route of the last SUM_FAST aggregation on this engine: the number of (line, disparity chunk) tasks the float-pair
+        passes redid behind the fixed-point sweeps (0 = none), or -1 when they took over whole sweeps."""
+        v = C.c_int32(0)
+        self._ck(self.lib.smt_aggregate_fast_status(self.h, C.byref(v)))
+        return int(v.value)
+
     # ------------------------------------------------------------------ CrossArm / CBLSM
     def ad_cost(self, left, right, D, view=0):
         """CBLSM ComputeAD (view 0) / ComputeADRight (view 1) from uint8 grey images."""
@@ -388,27 +395,31 @@ class Engine:
         self._ck(self.lib.smt_sad(self.h, pl, pr, Hp, Wp, D, winsize, int(bool(right_view)), pd, pc, a.space))
         return (disp, costs) if want_costs else disp
 
-    def ncc(self, left, right, D, win_size=10):
-        """NCC_algorithem (NCC/NCC.h:69)."""
+    def ncc(self, left, right, D, win_size=10, want_costs: bool = False):
+        """NCC_algorithem (NCC/NCC.h:69); want_costs adds ComputeCost's value per (pixel, d) as float64 [H][W][D]."""
         a = _Args(self, left, right)
         H, W = left.shape
         pl = a.inp(left, np.uint8, (H, W))
         pr = a.inp(right, np.uint8, (H, W))
         disp, pd = a.out((H, W), np.int32)
-        self._ck(self.lib.smt_ncc(self.h, pl, pr, H, W, win_size, D, pd, a.space))
-        return disp
+        costs, pc = a.out((H, W, D), np.float64, want_costs)
+        self._ck(self.lib.smt_ncc(self.h, pl, pr, H, W, win_size, D, pd, pc, a.space))
+        return (disp, costs) if want_costs else disp
 
-    def asw(self, left_padded, right_padded, D, win_size=11, space_sigma=50.0, color_sigma=30.0, T=40, right_view=False):
-        """AdaptiveSupportWeight / AdaptiveSupportWeightRight (ASW/ASW.h:329,382) on replicate-padded grey images."""
+    def asw(self, left_padded, right_padded, D, win_size=11, space_sigma=50.0, color_sigma=30.0, T=40, right_view=False,
+            want_costs: bool = False):
+        """AdaptiveSupportWeight / AdaptiveSupportWeightRight (ASW/ASW.h:329,382) on replicate-padded grey images;
+        want_costs adds the per-pixel costVolume rows as float32 [H][W][D]."""
         a = _Args(self, left_padded, right_padded)
         Hp, Wp = left_padded.shape
         pad = win_size + 1
         pl = a.inp(left_padded, np.uint8, (Hp, Wp))
         pr = a.inp(right_padded, np.uint8, (Hp, Wp))
         disp, pd = a.out((Hp - 2 * pad, Wp - 2 * pad), np.float32)
+        costs, pc = a.out((Hp - 2 * pad, Wp - 2 * pad, D), np.float32, want_costs)
         self._ck(self.lib.smt_asw(self.h, pl, pr, Hp, Wp, win_size, D, float(space_sigma), float(color_sigma), int(T),
-                                  int(bool(right_view)), pd, a.space))
-        return disp
+                                  int(bool(right_view)), pd, pc, a.space))
+        return (disp, costs) if want_costs else disp
 
     def asw_crosscheck(self, disp_left, disp_right):
         a = _Args(self, disp_left, disp_right)

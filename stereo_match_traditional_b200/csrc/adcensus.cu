@@ -289,7 +289,7 @@ smt_status_t smt_adcensus_cost(smt_ctx* ctx, const float* left, const float* rig
     SMT_REQUIRE(ctx, left && right && cost, SMT_ERR_INVALID_ARG, "smt_adcensus_cost: null image or cost pointer");
     SMT_REQUIRE(ctx, rows > 0 && cols > 0 && D > 0 && (view == 0 || view == 1), SMT_ERR_INVALID_ARG,
                 "smt_adcensus_cost: rows, cols, D must be positive and view 0 or 1");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols, nvol = npix * D;
     Marshal ms(ctx, space);
     const float* dl = ms.in(left, npix);
@@ -316,7 +316,7 @@ smt_status_t smt_census9x7_u64(smt_ctx* ctx, const float* img, int32_t rows, int
                                smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, img && out && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_census9x7_u64: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* di = ms.in(img, npix);
@@ -335,7 +335,7 @@ smt_status_t smt_wta_first_min(smt_ctx* ctx, const float* vol, int32_t rows, int
                                smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, vol && disp && rows > 0 && cols > 0 && D > 0, SMT_ERR_INVALID_ARG, "smt_wta_first_min: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* dv = ms.in(vol, npix * D);

@@ -48,6 +48,9 @@ struct smt_ctx {
     // exp LUT cache (host libm values, AD-Census.h:287-288)
     float lut_sigmaC = -1.f, lut_sigmaS = -1.f;
     float* d_lut = nullptr;  // 256 AD entries + 64 census entries
+    int* d_flags = nullptr;  // small device scratch ints (arm-length reduction)
+    int* d_redo = nullptr;   // redo state of the SMT_SUM_FAST aggregation (FX_ST_*), d_redo_cap list entries
+    size_t d_redo_cap = 0;
     // pinned staging for small host<->device scalars
     int32_t* h_pinned = nullptr;
 };
@@ -55,6 +58,22 @@ struct smt_ctx {
 smt_status_t smt_fail(smt_ctx* ctx, smt_status_t st, const char* fmt, ...);
 void* smt_pool_get(smt_ctx* ctx, size_t bytes);
 void smt_pool_put(smt_ctx* ctx, void* p);
+
+// Makes `device` current for the scope and restores the caller's device afterwards, so that an entry point never
+// changes the host framework's current device behind its back.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // RAII device buffer from the context's pool.
 struct DevBuf {
@@ -114,6 +133,14 @@ struct StageTimer {
     DevBuf name((ctx), (bytes));                                                                     \
     if (((size_t)(bytes)) != 0 && !name.ok())                                                        \
     return smt_fail((ctx), SMT_ERR_OOM, "device allocation of %zu bytes", (size_t)(bytes))
+
+// Redo state of a SMT_SUM_FAST aggregation, device ints shared by the fixed-point kernels (cross_agg_fx.cu, writers) and
+// the float-pair passes queued behind them (cross_agg_seq.cu, readers): [ESCALATED] the float-pair passes take whole
+// sweeps from now on, [COUNT] (line, disparity chunk) tasks on this sweep's redo list, [LIMIT] list length beyond which
+// ESCALATED is raised, [TOTAL] tasks listed over all sweeps of the aggregation, [LIST..] the list.
+enum { FX_ST_ESCALATED = 0, FX_ST_COUNT = 1, FX_ST_LIMIT = 2, FX_ST_TOTAL = 3, FX_ST_LIST = 4 };
+// the context's redo state, large enough for `ntasks` list entries (grow-only; contents are lost when it grows)
+int* smt_redo_state(smt_ctx* ctx, size_t ntasks);
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 

@@ -297,13 +297,7 @@ smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const 
     if (vec4) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
         float4* d4 = reinterpret_cast<float4*>(dst);
-        static const bool one_pos = getenv("SMT_EXACT_1POS") != nullptr;  // the four-disparity, one-position kernel
-        if (one_pos) {
-            if (horiz)
-                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<true>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
-            else
-                SMT_LAUNCH(ctx, agg_pass_exact4_kernel<false>, grid4, 256, 0, s4, d4, arms, s, H, W, D / 4);
-        } else {
+        {
             const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + EXACT_NP - 1) / EXACT_NP) * (D / 4);
             if (horiz)
                 SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
@@ -379,6 +373,24 @@ static smt_status_t volume_nonneg_max(smt_ctx* ctx, const float* vol, size_t n, 
     return SMT_OK;
 }
 
+// longest arm in a {left,right,top,bottom} map (host value; synchronises the stream)
+__global__ void __launch_bounds__(256) arms_max_kernel(const unsigned* __restrict__ arms, size_t npix, int* __restrict__ out) {
+    unsigned m = 0u;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (size_t)gridDim.x * blockDim.x) m = __vmaxu4(m, arms[k]);
+    m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (int)m);
+}
+smt_status_t k_arms_max(smt_ctx* ctx, const uint8_t* arms8, size_t npix, int* longest) {
+    int* slot = ctx->d_flags + 1;
+    SMT_CUDA(ctx, cudaMemsetAsync(slot, 0, sizeof(int), ctx->stream));
+    SMT_LAUNCH(ctx, arms_max_kernel, ctx->sm_count * 4, 256, 0, reinterpret_cast<const unsigned*>(arms8), npix, slot);
+    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *longest = ctx->h_pinned[0];
+    return SMT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- C ABI
 extern "C" {
 
@@ -386,7 +398,7 @@ smt_status_t smt_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int3
                             int32_t t2, uint8_t* arms_out, uint16_t* sup_hfirst, uint16_t* sup_vfirst, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, bgr && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_cross_arms: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const uint8_t* dbgr = ms.in(bgr, npix * 3);
@@ -411,7 +423,7 @@ smt_status_t smt_aggregate_cross(smt_ctx* ctx, const uint8_t* bgr, const float* 
                 "smt_aggregate_cross: unknown sum mode");
     SMT_REQUIRE(ctx, mode != SMT_SUM_FAST || L1 <= 34, SMT_ERR_UNSUPPORTED,
                 "smt_aggregate_cross: SMT_SUM_FAST tiles assume arms <= 34 (cross_L1 <= 34, the reference default)");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols, nvol = npix * D;
     Marshal ms(ctx, space);
     const uint8_t* dbgr = ms.in(bgr, npix * 3);

@@ -19,8 +19,6 @@
 // bias keeps the FastTwoSum error term exact), general TwoSum pair otherwise; window sums are exact to ~2^-46 and
 // rounded once.  The division by the support count is the correctly rounded quotient (Markstein's residual step on the
 // correctly rounded reciprocal), i.e. the same bits as the reference's IEEE `cost / count` (:389).
-#include <string>
-
 #include "common.cuh"
 
 // Development switches for the ablation runs quoted in DESIGN.md (all off in the product build):
@@ -137,7 +135,7 @@ __device__ __forceinline__ float key2f_(unsigned k) { return __uint_as_float(k ^
 // (value, d) pair per position and d-chunk; wta_reduce_kernel finishes the arg-min over the chunks.
 template <bool NONNEG, bool HAS_SUP, bool EDGE, bool WTA, int CSTEP = 0>
 __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len, bool act,
-                                          const float* __restrict__ src_next, float* __restrict__ dst_first, long long step_rt,
+                                          const float* src_next, float* dst_first, long long step_rt,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
                                           float2* __restrict__ wta_first, long long wta_step, int d, int zero) {
@@ -304,9 +302,11 @@ constexpr int SEQ_CTAS_PER_SM = 12 / SEQ_WARPS > 0 ? 12 / SEQ_WARPS : 1;
 constexpr int SEQ_SMEM_PER_WARP = SEQ_RING_SLOTS * 256;  // the descriptors live in a static array
 
 template <bool NONNEG, bool HAS_SUP, bool WTA, int CSTEP = 0>
-__global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kernel(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kernel(const float* in, float* out,  // may alias: a redo of a fused pair runs its first pass in place
+                                                    
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
-                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero, int tmaps) {
+                                                     int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero, int tmaps,
+                                                     const int* __restrict__ redo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
@@ -314,7 +314,13 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
     __shared__ Desc s_desc_all[SEQ_WARPS][SEQ_CH];
     Desc* s_desc = s_desc_all[warp];
     const int nchunk = (D + 31) >> 5;
-    const long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
+    long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
+    // redo != nullptr: this launch is queued behind a fixed-point sweep (cross_agg_fx.cu) and only redoes the (line, chunk)
+    // tasks that sweep put on its list -- or every task once the sweep escalated
+    if (redo && *reinterpret_cast<const volatile int*>(redo + FX_ST_ESCALATED) == 0) {
+        if (wg >= *reinterpret_cast<const volatile int*>(redo + FX_ST_COUNT)) return;
+        wg = redo[FX_ST_LIST + wg];
+    }
     const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
     const int len = horiz ? W : H;
     if (line >= (horiz ? H : W)) return;  // whole warp; warps never synchronise with each other
@@ -375,559 +381,9 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
 #undef SMT_SEQ_STEP
 }
 
-// ================================================================================================ fused pass pair
-// Two consecutive passes along the SAME direction (the reference's order H,V | V,H | H,V | V,H contains V,V and H,H
-// pairs) in one walk: pass A's outputs are consumed, in order, as pass B's input, so the intermediate volume is never
-// written or read.  A-output j appears when the A-prefix has reached j+35; B-output i when the B-prefix (over A's
-// outputs) has reached i+35, i.e. 70 positions behind the loads.  Pass A is the second pass of an iteration (divides
-// by its support count), pass B the first pass of the next one (no division).  Ring B stores E_B[j] at slot
-// (j+35) mod 96 so that, like ring A, every store inside a chunk has a compile-time offset.
-constexpr int SEQ2_CH = 32, SEQ2_R = 96;  // the fused walk keeps the 32-position chunks and 96-entry rings
-struct Prefetched2 {
-    unsigned armw_a, armw_b;
-    int cnt_a;
-};
-
-template <bool NONNEG, bool EDGE>
-__device__ __forceinline__ void seq2_chunk(pair2& acc_a, pair2& acc_b, Prefetched2& pre, float (&vuse)[SEQ2_CH], float (&vload)[SEQ2_CH],
-                                           int tb, int len, bool act, const float* __restrict__ src_next, float* __restrict__ dst_first,
-                                           long long step, long long pbase, long long pstride, int horiz,
-                                           const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_a,
-                                           unsigned char* ring_b, Desc* desc_a, Desc* desc_b, int lane) {
-    {
-        const float* p = src_next;
-#pragma unroll
-        for (int k = 0; k < SEQ2_CH; ++k) {
-            if (EDGE)
-                vload[k] = (tb + 2 * SEQ2_CH + k < len && act) ? __ldcs(p) : 0.f;
-            else
-                vload[k] = __ldcs(p);
-            p += step;
-        }
-    }
-    {
-        const int ja = tb - SEQ_LOOK + lane, ib = ja - SEQ_LOOK;
-        Desc da{0u, 0u, 1.f, 1.f}, db{0u, 0u, 1.f, 1.f};
-        if (!EDGE || (ja >= 0 && ja < len)) {
-            const unsigned aw = horiz ? (pre.armw_a & 0xffffu) : (pre.armw_a >> 16);
-            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            da.offa = (unsigned)(max(ja - lo, 0) % SEQ2_R) * 256u;
-            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQ2_R) * 256u;
-            da.cnt = (float)pre.cnt_a;
-            da.rcp = __frcp_rn(da.cnt);
-        }
-        if (!EDGE || (ib >= 0 && ib < len)) {
-            const unsigned aw = horiz ? (pre.armw_b & 0xffffu) : (pre.armw_b >> 16);
-            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            db.offa = (unsigned)((max(ib - lo, 0) + SEQ_LOOK) % SEQ2_R) * 256u;          // E_B[j] lives at slot (j+35) mod R
-            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQ_LOOK) % SEQ2_R) * 256u;
-        }
-        const int jn = ja + SEQ2_CH, in_ = ib + SEQ2_CH;
-        pre.armw_a = pre.armw_b = 0u;
-        pre.cnt_a = 1;
-        if (jn >= 0 && jn < len) {
-            const long long pix = pbase + pstride * jn;
-            pre.armw_a = __ldg(arms + pix);
-            pre.cnt_a = (int)__ldg(sup_a + pix);
-        }
-        if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_);
-        __syncwarp();
-        desc_a[lane] = da;
-        desc_b[lane] = db;
-        __syncwarp();
-    }
-    const unsigned woff = (unsigned)(tb % SEQ2_R) * 256u;
-    unsigned char* wa = ring_a + woff;  // slot of E_A[tb]
-    unsigned char* wb = ring_b + woff;  // slot of E_B[tb-35]
-    float* dp = dst_first;              // output position tb - 70
-#pragma unroll
-    for (int k = 0; k < SEQ2_CH; ++k) {
-        *reinterpret_cast<float2*>(wa + k * 256) = make_float2(acc_a.a, acc_a.b);  // E_A[tb+k]
-        acc_a = pre_add<NONNEG>(acc_a, vuse[k]);
-        if ((k & 7) == 7) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int kk = k - 7 + u;
-                // ---- pass A output j = tb+kk-35, fed straight into pass B's prefix
-                float a = 0.f;
-                if (!EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len)) {
-                    const Desc ds = desc_a[kk];
-                    const float2 ea = *reinterpret_cast<const float2*>(ring_a + ds.offa);
-                    const float2 eb = *reinterpret_cast<const float2*>(ring_a + ds.offb);
-                    a = div_by_count(__fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y)), ds.cnt, ds.rcp);
-                }
-                *reinterpret_cast<float2*>(wb + kk * 256) = make_float2(acc_b.a, acc_b.b);  // E_B[j]
-                acc_b = pre_add<NONNEG>(acc_b, a);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int kk = k - 7 + u;
-                // ---- pass B output i = tb+kk-70 (needs E_B up to i+35 = j, stored just above)
-                if (!EDGE || (tb - 2 * SEQ_LOOK + kk >= 0 && tb - 2 * SEQ_LOOK + kk < len)) {
-                    const Desc ds = desc_b[kk];
-                    const float2 ea = *reinterpret_cast<const float2*>(ring_b + ds.offa);
-                    const float2 eb = *reinterpret_cast<const float2*>(ring_b + ds.offb);
-                    const float r = __fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y));
-                    if (!EDGE || act) __stcs(dp, r);
-                }
-                dp += step;
-            }
-        }
-    }
-}
-
-constexpr int SEQ2_WARPS = 4;
-constexpr int SEQ2_SMEM_PER_WARP = 2 * SEQ2_R * 256 + 2 * SEQ2_CH * (int)sizeof(Desc);
-
-template <bool NONNEG>
-__global__ void __launch_bounds__(SEQ2_WARPS * 32) agg_seq2_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                                  const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a,
-                                                                  int H, int W, int D, int horiz, float bias_a, float bias_b) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)warp * SEQ2_SMEM_PER_WARP;
-    unsigned char* ring_a = base + lane * 8;
-    unsigned char* ring_b = base + SEQ2_R * 256 + lane * 8;
-    Desc* desc_a = reinterpret_cast<Desc*>(base + 2 * SEQ2_R * 256);
-    Desc* desc_b = desc_a + SEQ2_CH;
-    const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
-    const int nchunk = (D + 31) >> 5;
-    const long long wg = (long long)blockIdx.x * SEQ2_WARPS + warp;
-    const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
-    const int len = horiz ? W : H;
-    if (line >= (horiz ? H : W)) return;
-    const int d = chunk * 32 + lane;
-    const bool act = d < D;
-    const bool full = chunk * 32 + 32 <= D;
-    const long long pstride = horiz ? 1 : (long long)W;
-    const long long pbase = horiz ? (long long)line * W : (long long)line;
-    const long long step = pstride * D;
-    const float* src = in + pbase * D + (act ? d : 0);
-    float* dst = out + pbase * D + (act ? d : 0);
-
-    pair2 acc_a{NONNEG ? bias_a : 0.f, 0.f}, acc_b{NONNEG ? bias_b : 0.f, 0.f};
-    float va[SEQ2_CH], vb[SEQ2_CH], vc[SEQ2_CH];
-#pragma unroll
-    for (int k = 0; k < SEQ2_CH; ++k) {
-        va[k] = (k < len && act) ? __ldcs(src + step * k) : 0.f;
-        vb[k] = (SEQ2_CH + k < len && act) ? __ldcs(src + step * (SEQ2_CH + k)) : 0.f;
-    }
-    Prefetched2 pre{0u, 0u, 1};
-    const int nouter = (len + 2 * SEQ_LOOK + SEQ2_CH - 1) / SEQ2_CH;
-#define SMT_SEQ2_STEP(USE, LOAD)                                                                                             \
-    if (o < nouter) {                                                                                                        \
-        const int tb = o * SEQ2_CH;                                                                                           \
-        const float* src_next = src + step * (tb + 2 * SEQ2_CH);                                                              \
-        float* dst_first = dst + step * (tb - 2 * SEQ_LOOK);                                                                 \
-        if (full && tb - 2 * SEQ_LOOK >= 0 && tb + 3 * SEQ2_CH <= len)                                                        \
-            seq2_chunk<NONNEG, false>(acc_a, acc_b, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride, \
-                                      horiz, arms, sup_a, ring_a, ring_b, desc_a, desc_b, lane);                             \
-        else                                                                                                                 \
-            seq2_chunk<NONNEG, true>(acc_a, acc_b, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, pbase, pstride,  \
-                                     horiz, arms, sup_a, ring_a, ring_b, desc_a, desc_b, lane);                              \
-        ++o;                                                                                                                 \
-    }
-    for (int o = 0; o < nouter;) {
-        SMT_SEQ2_STEP(va, vc)
-        SMT_SEQ2_STEP(vb, va)
-        SMT_SEQ2_STEP(vc, vb)
-    }
-#undef SMT_SEQ2_STEP
-}
-
-template <bool NONNEG>
-static smt_status_t launch_seq2(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
-                                int horiz, float bias_a, float bias_b) {
-    constexpr size_t smem = (size_t)SEQ2_WARPS * SEQ2_SMEM_PER_WARP;
-    static bool attr_set_dev[64] = {};  // function attributes are per device
-    bool& attr_set = attr_set_dev[ctx->device & 63];
-    if (!attr_set) {
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seq2_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
-    SMT_LAUNCH(ctx, (agg_seq2_kernel<NONNEG>), cdiv(nwarps, SEQ2_WARPS), SEQ2_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
-               bias_b);
-    return SMT_OK;
-}
-
-// ================================================================================================ fused pair, half-warp roles
-// The same two passes (A divides, B does not) in one walk at the occupancy of a single pass: a warp covers 16 disparities;
-// lanes 0-15 run pass A on them, lanes 16-31 run pass B on the same 16, every lane owns ONE ring column.  All lanes execute
-// one instruction stream -- ring store, prefix step, descriptor read, two ring reads, difference, division (B divides by
-// 1, which is exact) -- and differ only in where the prefix input comes from (A: the volume; B: its partner's outputs of
-// the previous group of 8, handed over by shuffle) and in who touches memory (A lanes load, B lanes store; 64-byte rows).
-// With chunk base tb and step kk: A stores E_A[tb+kk] and emits j = tb+kk-35; B consumes A-output tb+kk-43, stores
-// E_B[tb+kk-43] in the slot of the same index (so E_B[q] lives at slot (q+43) mod 96) and emits i = tb+kk-78.
-constexpr int SEQH_CH = 32, SEQH_R = 96, SEQH_WARPS = 8;  // this kernel keeps 32-position chunks and a 96-entry ring
-constexpr int SEQH_LAG = SEQ_LOOK + SEQ_G;        // 43: B's prefix position trails A's by this much
-constexpr int SEQH_LOOKB = SEQH_LAG + SEQ_LOOK;   // 78: B's output position trails A's prefix position by this much
-struct PrefetchedH {
-    unsigned armw_a, armw_b;
-    int cnt_a;
-};
-
-template <bool NONNEG, bool EDGE>
-__device__ __forceinline__ void seqh_chunk(pair2& acc, PrefetchedH& pre, float (&rin)[SEQ_G], float (&vuse)[SEQH_CH], float (&vload)[SEQH_CH],
-                                           int tb, int len, bool act, bool isb, const float* __restrict__ src_next,
-                                           float* __restrict__ dst_first, long long step, long long pbase, long long pstride, int horiz,
-                                           const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup_a, unsigned char* ring_col,
-                                           Desc* desc, int lane, int zero) {
-    // same order as seq_chunk: consume what the previous chunk fetched, then issue this chunk's loads, then the rest
-    {
-        const int ja = tb - SEQ_LOOK + lane, ib = tb - SEQH_LOOKB + lane;
-        Desc da{0u, 0u, 1.f, 1.f}, db{0u, 0u, 1.f, 1.f};
-        if (!EDGE || (ja >= 0 && ja < len)) {
-            const unsigned aw = horiz ? (pre.armw_a & 0xffffu) : (pre.armw_a >> 16);
-            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            da.offa = (unsigned)(max(ja - lo, 0) % SEQH_R) * 256u;
-            da.offb = (unsigned)(min(ja + hi + 1, len) % SEQH_R) * 256u;
-            da.cnt = (float)pre.cnt_a;
-            da.rcp = __frcp_rn(da.cnt);
-        }
-        if (!EDGE || (ib >= 0 && ib < len)) {
-            const unsigned aw = horiz ? (pre.armw_b & 0xffffu) : (pre.armw_b >> 16);
-            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            db.offa = (unsigned)((max(ib - lo, 0) + SEQH_LAG) % SEQH_R) * 256u;
-            db.offb = (unsigned)((min(ib + hi + 1, len) + SEQH_LAG) % SEQH_R) * 256u;
-        }
-        __syncwarp();
-        desc[2 * lane] = da;  // interleaved so that the two halves of the warp read different banks
-        desc[2 * lane + 1] = db;
-        __syncwarp();
-    }
-    unsigned char* wbase = ring_col + (unsigned)(tb % SEQH_R) * 256u;
-    const Desc* dsel = desc + (isb ? 1 : 0);
-    float* dp = dst_first;  // B output position tb - 78 (only B lanes store)
-    *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);
-    acc = pre_add<NONNEG>(acc, isb ? rin[0] : vuse[0]);
-    const int dep = __float_as_int(acc.a) & zero;
-    {
-        const float* p = src_next + dep;
-#pragma unroll
-        for (int k = 0; k < SEQH_CH; ++k) {
-            if (EDGE)
-                vload[k] = (!isb && tb + SEQH_CH + k < len && act) ? __ldcs(p) : 0.f;
-            else
-                vload[k] = !isb ? __ldcs(p) : 0.f;
-            p += step;
-        }
-#if SMT_SEQ_L2PF > 0
-        {
-            const int q = tb + (1 + SMT_SEQ_L2PF) * SEQH_CH + lane;
-            if (q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQH_CH + lane)));
-        }
-#endif
-        const int jn = tb - SEQ_LOOK + lane + SEQH_CH, in_ = tb - SEQH_LOOKB + lane + SEQH_CH;
-        pre.armw_a = pre.armw_b = 0u;
-        pre.cnt_a = 1;
-        if (jn >= 0 && jn < len) {
-            const long long pix = pbase + pstride * jn + dep;
-            pre.armw_a = __ldg(arms + pix);
-            pre.cnt_a = (int)__ldg(sup_a + pix);
-        }
-        if (in_ >= 0 && in_ < len) pre.armw_b = __ldg(arms + pbase + pstride * in_ + dep);
-    }
-#pragma unroll
-    for (int k = 0; k < SEQH_CH; ++k) {
-        if (k > 0) {
-            *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);  // E_A[tb+k] / E_B[tb+k-43]
-            acc = pre_add<NONNEG>(acc, isb ? rin[k & (SEQ_G - 1)] : vuse[k]);
-        }
-        if ((k & (SEQ_G - 1)) == SEQ_G - 1) {
-#pragma unroll
-            for (int u = 0; u < SEQ_G; ++u) {
-                const int kk = k - (SEQ_G - 1) + u;
-                const Desc ds = dsel[2 * kk];
-                const float2 ea = *reinterpret_cast<const float2*>(ring_col + ds.offa);
-                const float2 eb = *reinterpret_cast<const float2*>(ring_col + ds.offb);
-                float r = div_by_count(__fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y)), ds.cnt, ds.rcp);
-                if (EDGE) {
-                    const int ja = tb - SEQ_LOOK + kk, ib = tb - SEQH_LOOKB + kk;
-                    if (isb) {
-                        if (ib >= 0 && ib < len && act) __stcs(dp, r);
-                    } else if (ja < 0 || ja >= len) {
-                        r = 0.f;  // positions outside the line feed zeros into pass B's prefix
-                    }
-                } else if (isb) {
-                    __stcs(dp, r);
-                }
-                dp += step;
-                rin[u] = __shfl_sync(0xffffffffu, r, lane & 15);  // B lanes receive their partner's A output
-            }
-        }
-    }
-}
-
-template <bool NONNEG>
-__global__ void __launch_bounds__(SEQH_WARPS * 32) agg_seqh_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                                 const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a, int H,
-                                                                 int W, int D, int horiz, float bias_a, float bias_b, int zero) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* s_ring = smem_raw + (size_t)warp * (SEQH_R * 256 + 2 * SEQH_CH * (int)sizeof(Desc));
-    Desc* s_desc = reinterpret_cast<Desc*>(s_ring + SEQH_R * 256);
-    const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
-    const int nh = (D + 15) >> 4;  // 16-disparity groups per line
-    const long long wg = (long long)blockIdx.x * SEQH_WARPS + warp;
-    const int line = (int)(wg / nh), hc = (int)(wg - (long long)line * nh);
-    const int len = horiz ? W : H;
-    if (line >= (horiz ? H : W)) return;
-    const bool isb = lane >= 16;
-    const int d = hc * 16 + (lane & 15);
-    const bool act = d < D;
-    const bool full = hc * 16 + 16 <= D;
-    const long long pstride = horiz ? 1 : (long long)W;
-    const long long pbase = horiz ? (long long)line * W : (long long)line;
-    const long long step = pstride * D;
-    const float* src = in + pbase * D + (act ? d : 0);
-    float* dst = out + pbase * D + (act ? d : 0);
-    unsigned char* ring_col = s_ring + lane * 8;
-
-    pair2 acc{NONNEG ? (isb ? bias_b : bias_a) : 0.f, 0.f};
-    float rin[SEQ_G];
-#pragma unroll
-    for (int u = 0; u < SEQ_G; ++u) rin[u] = 0.f;
-    float va[SEQH_CH], vb[SEQH_CH];
-#pragma unroll
-    for (int k = 0; k < SEQH_CH; ++k) va[k] = (!isb && k < len && act) ? __ldcs(src + step * k) : 0.f;
-    PrefetchedH pre{0u, 0u, 1};
-    const int nouter = (len + SEQH_LOOKB + SEQH_CH - 1) / SEQH_CH;
-#define SMT_SEQH_STEP(USE, LOAD)                                                                                              \
-    if (o < nouter) {                                                                                                         \
-        const int tb = o * SEQH_CH;                                                                                            \
-        const float* src_next = src + step * (tb + SEQH_CH);                                                                   \
-        float* dst_first = dst + step * (tb - SEQH_LOOKB);                                                                    \
-        if (full && tb - SEQH_LOOKB >= 0 && tb + 2 * SEQH_CH <= len)                                                           \
-            seqh_chunk<NONNEG, false>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride, \
-                                      horiz, arms, sup_a, ring_col, s_desc, lane, zero);                                      \
-        else                                                                                                                  \
-            seqh_chunk<NONNEG, true>(acc, pre, rin, USE, LOAD, tb, len, act, isb, src_next, dst_first, step, pbase, pstride,  \
-                                     horiz, arms, sup_a, ring_col, s_desc, lane, zero);                                       \
-        ++o;                                                                                                                  \
-    }
-    for (int o = 0; o < nouter;) {
-        SMT_SEQH_STEP(va, vb)
-        SMT_SEQH_STEP(vb, va)
-    }
-#undef SMT_SEQH_STEP
-}
-
-template <bool NONNEG>
-static smt_status_t launch_seqh(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
-                                int horiz, float bias_a, float bias_b) {
-    constexpr size_t smem = (size_t)SEQH_WARPS * (SEQH_R * 256 + 2 * SEQH_CH * sizeof(Desc));
-    static bool attr_set_dev[64] = {};  // function attributes are per device
-    bool& attr_set = attr_set_dev[ctx->device & 63];
-    if (!attr_set) {
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqh_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const long long nwarps = (long long)(horiz ? H : W) * ((D + 15) / 16);
-    SMT_LAUNCH(ctx, (agg_seqh_kernel<NONNEG>), cdiv(nwarps, SEQH_WARPS), SEQH_WARPS * 32, smem, in, out, arms, sup_a, H, W, D, horiz, bias_a,
-               bias_b, 0);
-    return SMT_OK;
-}
-
-// ================================================================================================ fused pair, warp pair
-// Two passes along the same direction (A divides, B does not) by a PAIR of warps of one block: warp 0 runs pass A on a
-// (line, 32-disparity) task exactly like agg_seq_kernel but puts its outputs into a double-buffered 2 x 3 KB queue in
-// shared memory instead of the volume; warp 1 runs pass B with the queue as its input and writes the volume.  One
-// __syncthreads per chunk hands a buffer over.  B's prefix positions are A's output positions, chunk o of B covers
-// positions 24o-35 .. 24o-12 (what A emitted in its chunk o), so E_B[q] lives at ring slot (q+35) mod 72 and every ring
-// store of B has the same compile-time offset as A's; B emits i = 24o-70+k.  Per pair: two rings + queue = 42 KB, five
-// pairs per SM.
-constexpr int SEQP_LOOKB = 2 * SEQ_LOOK;  // 70
-struct PrefetchedP {
-    unsigned armw;
-    int cnt;
-};
-
-// ROLE 1 = producer (pass A), 2 = consumer (pass B)
-template <bool NONNEG, int ROLE, bool EDGE>
-__device__ __forceinline__ void seqp_chunk(pair2& acc, PrefetchedP& pre, float (&vuse)[SEQ_CH], float (&vload)[SEQ_CH], int tb, int len,
-                                           bool act, const float* __restrict__ src_next, float* __restrict__ dst_first, long long step,
-                                           long long mbase, long long mstride, int horiz, const unsigned* __restrict__ arms,
-                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, float* queue,
-                                           int lane, int zero) {
-    constexpr int LOOK = ROLE == 1 ? SEQ_LOOK : SEQP_LOOKB;      // output position = tb - LOOK + k
-    constexpr int SHIFT = ROLE == 1 ? 0 : SEQ_LOOK;              // E[q] lives at slot (q + SHIFT) mod R
-    const long long step_b = step * 4;
-    {
-        const int j = tb - LOOK + lane;
-        Desc ds{0u, 0u, 1.f, 1.f};
-        if (lane < SEQ_CH && (!EDGE || (j >= 0 && j < len))) {
-            const unsigned aw = horiz ? (pre.armw & 0xffffu) : (pre.armw >> 16);
-            const int lo = (int)(aw & 0xffu), hi = (int)(aw >> 8);
-            ds.offa = (unsigned)((max(j - lo, 0) + SHIFT) % SEQ_R) * 256u;
-            ds.offb = (unsigned)((min(j + hi + 1, len) + SHIFT) % SEQ_R) * 256u;
-            if (ROLE == 1) {
-                ds.cnt = (float)pre.cnt;
-                ds.rcp = __frcp_rn(ds.cnt);
-            }
-        }
-        __syncwarp();
-        if (lane < SEQ_CH) desc[lane] = ds;
-        __syncwarp();
-    }
-    unsigned char* wbase = ring_col + (unsigned)(tb % SEQ_R) * 256u;
-    char* dp = reinterpret_cast<char*>(dst_first);  // ROLE 2: output position tb - 70
-    if (ROLE == 2) {
-#pragma unroll
-        for (int k = 0; k < SEQ_CH; ++k) vuse[k] = queue[k * 32 + lane];
-    }
-    *reinterpret_cast<float2*>(wbase) = make_float2(acc.a, acc.b);
-    acc = pre_add<NONNEG>(acc, vuse[0]);
-    const int dep = __float_as_int(acc.a) & zero;
-    {
-        if (ROLE == 1) {
-            const char* p = reinterpret_cast<const char*>(src_next + dep);
-#pragma unroll
-            for (int k = 0; k < SEQ_CH; ++k) {
-                if (EDGE)
-                    vload[k] = (tb + SEQ_CH + k < len && act) ? __ldcs(reinterpret_cast<const float*>(p)) : 0.f;
-                else
-                    vload[k] = __ldcs(reinterpret_cast<const float*>(p));
-                p += step_b;
-            }
-#if SMT_SEQ_L2PF > 0
-            const int q = tb + (1 + SMT_SEQ_L2PF) * SEQ_CH + lane;
-            if (lane < SEQ_CH && q < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_next + dep + step * (SMT_SEQ_L2PF * SEQ_CH + lane)));
-#endif
-        }
-        const int jn = tb - LOOK + lane + SEQ_CH;
-        pre.armw = 0u;
-        pre.cnt = 1;
-        if (lane < SEQ_CH && jn >= 0 && jn < len) {
-            const long long pix = mbase + mstride * jn + dep;
-            pre.armw = __ldg(arms + pix);
-            if (ROLE == 1) pre.cnt = (int)__ldg(sup + pix);
-        }
-    }
-    {
-        Desc dsc[SEQ_CH];
-        float2 ea[SEQ_CH], eb[SEQ_CH];
-#pragma unroll
-        for (int u = 0; u < SEQ_DLAG; ++u) dsc[u] = desc[u];
-#pragma unroll
-        for (int k = 0; k < SEQ_CH + SEQ_RLAG; ++k) {
-            if (k < SEQ_CH) {
-                if (k > 0) {
-                    *reinterpret_cast<float2*>(wbase + k * 256) = make_float2(acc.a, acc.b);
-                    acc = pre_add<NONNEG>(acc, vuse[k]);
-                }
-                ea[k] = *reinterpret_cast<const float2*>(ring_col + dsc[k].offa);
-                eb[k] = *reinterpret_cast<const float2*>(ring_col + dsc[k].offb);
-                if (k + SEQ_DLAG < SEQ_CH) dsc[k + SEQ_DLAG] = desc[k + SEQ_DLAG];
-            }
-            if (k >= SEQ_RLAG) {
-                const int kk = k - SEQ_RLAG;
-                const bool inside = !EDGE || (tb - LOOK + kk >= 0 && tb - LOOK + kk < len);  // warp-uniform
-                float r = __fadd_rn(__fsub_rn(eb[kk].x, ea[kk].x), __fsub_rn(eb[kk].y, ea[kk].y));
-                if (ROLE == 1) {
-                    r = div_by_count(r, dsc[kk].cnt, dsc[kk].rcp);
-                    queue[kk * 32 + lane] = (inside && (!EDGE || act)) ? r : 0.f;  // positions outside the line feed zeros into pass B
-                } else {
-                    if (inside && (!EDGE || act)) __stcs(reinterpret_cast<float*>(dp), r);
-                    dp += step_b;
-                }
-            }
-        }
-    }
-}
-
-constexpr int SEQP_SMEM = 2 * SEQ_R * 256 + 2 * SEQ_CH * 128;  // two rings + two queue buffers
-
-template <bool NONNEG>
-__global__ void __launch_bounds__(64, 5) agg_seqp_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                         const uchar4* __restrict__ arms4, const uint16_t* __restrict__ sup_a, int H, int W,
-                                                         int D, int horiz, float bias_a, float bias_b, int zero, int tmaps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ Desc s_desc_all[2][SEQ_CH];
-    const int lane = threadIdx.x & 31, role = 1 + (threadIdx.x >> 5);  // warp 0: pass A, warp 1: pass B
-    unsigned char* ring_col = smem_raw + (size_t)(role - 1) * SEQ_R * 256 + lane * 8;
-    float* queue = reinterpret_cast<float*>(smem_raw + 2 * SEQ_R * 256);  // [2][SEQ_CH][32]
-    Desc* s_desc = s_desc_all[role - 1];
-    const unsigned* arms = reinterpret_cast<const unsigned*>(arms4);
-    const int nchunk = (D + 31) >> 5;
-    const long long wg = blockIdx.x;
-    const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
-    const int len = horiz ? W : H;
-    const int d = chunk * 32 + lane;
-    const bool act = d < D;
-    const bool full = chunk * 32 + 32 <= D;
-    const long long pstride = horiz ? 1 : (long long)W;
-    const long long pbase = horiz ? (long long)line * W : (long long)line;
-    const long long step = pstride * D;
-    const float* src = in + pbase * D + (act ? d : 0);
-    float* dst = out + pbase * D + (act ? d : 0);
-    const long long mstride = (!horiz && tmaps) ? 1 : pstride;
-    const long long mbase = (!horiz && tmaps) ? (long long)line * H : pbase;
-
-    pair2 acc{NONNEG ? (role == 1 ? bias_a : bias_b) : 0.f, 0.f};
-    float va[SEQ_CH], vb[SEQ_CH];
-#pragma unroll
-    for (int k = 0; k < SEQ_CH; ++k) {
-        va[k] = (role == 1 && k < len && act) ? __ldcs(src + step * k) : 0.f;
-        vb[k] = 0.f;
-    }
-    PrefetchedP pre{0u, 1};
-    const int nouter = (len + SEQP_LOOKB + SEQ_CH - 1) / SEQ_CH;  // chunks of pass B; pass A keeps running (zeros) to feed them
-    // iteration it: A does its chunk `it` into queue buffer it&1, B does its chunk `it-1` from the buffer A filled last time
-#define SMT_SEQP_STEP(USE, LOAD)                                                                                                        \
-    if (it <= nouter) {                                                                                                                 \
-        if (role == 1) {                                                                                                                \
-            if (it < nouter) {                                                                                                          \
-                const int tb = it * SEQ_CH;                                                                                             \
-                const float* src_next = src + step * (tb + SEQ_CH);                                                                     \
-                float* qb = queue + (it & 1) * SEQ_CH * 32;                                                                             \
-                if (full && tb - SEQ_LOOK >= 0 && tb + 2 * SEQ_CH <= len)                                                               \
-                    seqp_chunk<NONNEG, 1, false>(acc, pre, USE, LOAD, tb, len, act, src_next, nullptr, step, mbase, mstride, horiz, arms, \
-                                                 sup_a, ring_col, s_desc, qb, lane, zero);                                              \
-                else                                                                                                                    \
-                    seqp_chunk<NONNEG, 1, true>(acc, pre, USE, LOAD, tb, len, act, src_next, nullptr, step, mbase, mstride, horiz, arms,  \
-                                                sup_a, ring_col, s_desc, qb, lane, zero);                                               \
-            }                                                                                                                           \
-        } else if (it >= 1) {                                                                                                           \
-            const int tb = (it - 1) * SEQ_CH;                                                                                           \
-            float* dst_first = dst + step * (tb - SEQP_LOOKB);                                                                          \
-            float* qb = queue + ((it - 1) & 1) * SEQ_CH * 32;                                                                           \
-            if (full && tb - SEQP_LOOKB >= 0 && tb - SEQP_LOOKB + SEQ_CH <= len)                                                        \
-                seqp_chunk<NONNEG, 2, false>(acc, pre, USE, LOAD, tb, len, act, nullptr, dst_first, step, mbase, mstride, horiz, arms,    \
-                                             sup_a, ring_col, s_desc, qb, lane, zero);                                                  \
-            else                                                                                                                        \
-                seqp_chunk<NONNEG, 2, true>(acc, pre, USE, LOAD, tb, len, act, nullptr, dst_first, step, mbase, mstride, horiz, arms,     \
-                                            sup_a, ring_col, s_desc, qb, lane, zero);                                                   \
-        }                                                                                                                               \
-        __syncthreads();                                                                                                                \
-        ++it;                                                                                                                           \
-    }
-    for (int it = 0; it <= nouter;) {
-        SMT_SEQP_STEP(va, vb)
-        SMT_SEQP_STEP(vb, va)
-    }
-#undef SMT_SEQP_STEP
-}
-
-template <bool NONNEG>
-static smt_status_t launch_seqp(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup_a, int H, int W, int D,
-                                int horiz, float bias_a, float bias_b, int tmaps) {
-    static bool attr_set_dev[64] = {};
-    bool& attr_set = attr_set_dev[ctx->device & 63];
-    if (!attr_set) {
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqp_kernel<NONNEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQP_SMEM));
-        SMT_CUDA(ctx, cudaFuncSetAttribute(agg_seqp_kernel<NONNEG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           (int)cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
-    }
-    const long long ntask = (long long)(horiz ? H : W) * ((D + 31) / 32);
-    SMT_LAUNCH(ctx, (agg_seqp_kernel<NONNEG>), (unsigned)ntask, 64, SEQP_SMEM, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b, 0, tmaps);
-    return SMT_OK;
-}
-
 template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
-                               int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0) {
+                               int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0, const int* redo = nullptr) {
     constexpr size_t smem = (size_t)SEQ_WARPS * SEQ_SMEM_PER_WARP;
     static bool attr_set_dev[64] = {};  // function attributes are per device
     bool& attr_set = attr_set_dev[ctx->device & 63];
@@ -951,11 +407,11 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
             attr2 = true;
         }
         SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
-                   horiz, bias, wta_partial, 0, tmaps);
+                   horiz, bias, wta_partial, 0, tmaps, redo);
         return SMT_OK;
     }
     SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
-               bias, wta_partial, 0, tmaps);
+               bias, wta_partial, 0, tmaps, redo);
     return SMT_OK;
 }
 
@@ -963,15 +419,20 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
 
 smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const uint8_t* arms8, const uint16_t* s, int H, int W, int D,
                               int horiz);  // cross_agg.cu
+smt_status_t k_arms_max(smt_ctx* ctx, const uint8_t* arms8, size_t npix, int* longest);  // cross_agg.cu (synchronises)
+bool fx_quantum(float vmax, float* inv_q, float* q);  // cross_agg_fx.cu
+smt_status_t k_agg_fx_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
+                           int horiz, int tmaps, float inv_q, float q, int* state);
+smt_status_t k_fx_state_reset(smt_ctx* ctx, int* state, bool new_aggregation, size_t ntasks);
 
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                            int horiz, bool nonneg, float bias, int tmaps) {
+                            int horiz, bool nonneg, float bias, int tmaps, const int* redo) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     if (nonneg)
-        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps)
-                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps);
-    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps)
-               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps);
+        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo)
+                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo);
+    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo)
+               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo);
 }
 
 // [H][W] -> [W][H] copies of the arm words and of one support-count map for the vertical walks
@@ -1004,44 +465,17 @@ smt_status_t k_transpose_maps(smt_ctx* ctx, const uint8_t* arms8, const uint16_t
     return SMT_OK;
 }
 
-// chunk partials -> first-minimum disparity (ascending chunks, strict '<': AD-Census.h:359-372)
-__global__ void __launch_bounds__(256) wta_reduce_kernel(const float2* __restrict__ partial, size_t npix, int nchunk, float* __restrict__ disp) {
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
-    float2 best = partial[p * nchunk];
-    for (int c = 1; c < nchunk; ++c) {
-        const float2 v = partial[p * nchunk + c];
-        if (v.x < best.x) best = v;
+// one sweep's redo state: the list is emptied; a new aggregation also clears the escalation and the running total
+smt_status_t k_fx_state_reset(smt_ctx* ctx, int* state, bool new_aggregation, size_t ntasks) {
+    const int limit = (int)(ntasks / 4);
+    if (new_aggregation) {
+        const int init[4] = {0, 0, limit, 0};
+        for (int k = 0; k < 4; ++k) ctx->h_pinned[32 + k] = init[k];
+        SMT_CUDA(ctx, cudaMemcpyAsync(state, ctx->h_pinned + 32, 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        SMT_CUDA(ctx, cudaMemsetAsync(state + FX_ST_COUNT, 0, sizeof(int), ctx->stream));
     }
-    disp[p] = best.y;
-}
-
-// last (dividing) pass of an aggregation whose only consumer is a winner-take-all: the volume is never written
-smt_status_t k_agg_seq_pass_wta(smt_ctx* ctx, const float* in, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D, int horiz,
-                                float bias, float* disp) {
-    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
-    const int nchunk = (D + 31) / 32;
-    const size_t npix = (size_t)H * W;
-    SMT_ALLOC(ctx, part, npix * nchunk * sizeof(float2));
-    SMT_TRY((launch_seq<true, true, true>(ctx, in, nullptr, arms, sup, H, W, D, horiz, bias, part.as<float2>())));
-    SMT_LAUNCH(ctx, wta_reduce_kernel, cdiv((long long)npix, 256), 256, 0, part.as<float2>(), npix, nchunk, disp);
     return SMT_OK;
-}
-
-// pass A (divides by sup_a) followed by pass B (no division) along the same direction, in one walk
-smt_status_t k_agg_seq_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup_a, int H, int W, int D,
-                            int horiz, bool nonneg, float bias_a, float bias_b, int tmaps) {
-    const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
-    // SMT_AGG_FUSE: "pair" (or 1) = producer / consumer warp pair, "hw" = half-warp roles, "rings" = two rings per lane
-    static const std::string how = getenv("SMT_AGG_FUSE") ? getenv("SMT_AGG_FUSE") : "";
-    if (how == "rings" && !tmaps)
-        return nonneg ? launch_seq2<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
-                      : launch_seq2<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
-    if (how == "hw" && !tmaps)
-        return nonneg ? launch_seqh<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b)
-                      : launch_seqh<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b);
-    return nonneg ? launch_seqp<true>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b, tmaps)
-                  : launch_seqp<false>(ctx, in, out, arms, sup_a, H, W, D, horiz, bias_a, bias_b, tmaps);
 }
 
 // ---------------------------------------------------------------------------------------------- per-sweep C ABI (row bands)
@@ -1069,15 +503,43 @@ smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t swee
     int32_t horiz = 0, divides = 0;
     if (smt_cross_sweep_info(iters, sweep, &horiz, &divides) != SMT_OK)
         return smt_fail(ctx, SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: sweep %d outside 0..%d", sweep, 2 * iters - 1);
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     StageTimer t(ctx, ST_AGGREGATE);
     const bool hfirst = (sweep / 2) % 2 == 0;
     const uint16_t* sup = divides ? (hfirst ? sup_hfirst : sup_vfirst) : nullptr;
     if (mode == SMT_SUM_REFERENCE_ORDER) return k_agg_exact_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz);
+    SMT_REQUIRE(ctx, mode == SMT_SUM_FAST, SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: unknown sum mode");
     const bool nonneg = vmax > 0.f && vmax < 1e30f;
     float b = 1.f;
     while (nonneg && b < vmax) b *= 2.f;
-    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, divides ? b * 128.f : b, 0);
+    float inv_q = 0.f, q = 0.f;
+    const bool fx = nonneg && fx_quantum(vmax, &inv_q, &q);
+    const size_t ntasks = (size_t)(rows > cols ? rows : cols) * ((D + 31) / 32);
+    int* state = fx ? smt_redo_state(ctx, ntasks) : nullptr;
+    if (fx && !state) return smt_fail(ctx, SMT_ERR_OOM, "smt_aggregate_cross_sweep: redo list allocation failed");
+    if (sweep == 0) {
+        // the streaming kernels keep 72 prefix entries per line: arms beyond 34 would wrap onto stale entries
+        int longest = 0;
+        SMT_TRY(k_arms_max(ctx, arms, (size_t)rows * cols, &longest));
+        if (longest > 34)
+            return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "smt_aggregate_cross_sweep: SMT_SUM_FAST supports arms <= 34, the maps hold %d", longest);
+    }
+    if (fx) {
+        SMT_TRY(k_fx_state_reset(ctx, state, sweep == 0, ntasks));
+        SMT_TRY(k_agg_fx_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, 0, inv_q, q, state));
+    }
+    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, divides ? b * 128.f : b, 0, state);
+}
+
+smt_status_t smt_aggregate_fast_status(smt_ctx* ctx, int32_t* used_float_pairs) {
+    if (!ctx || !used_float_pairs) return SMT_ERR_INVALID_ARG;
+    DeviceGuard dev_guard(ctx->device);
+    *used_float_pairs = 0;
+    if (!ctx->d_redo) return SMT_OK;  // no fast aggregation has run on this context
+    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_redo, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *used_float_pairs = ctx->h_pinned[FX_ST_ESCALATED] ? -1 : ctx->h_pinned[FX_ST_TOTAL];
+    return SMT_OK;
 }
 
 }  // extern "C"

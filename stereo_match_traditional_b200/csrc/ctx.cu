@@ -72,7 +72,7 @@ StageTimer::~StageTimer() {
 
 extern "C" {
 
-int32_t smt_abi_version(void) { return 1; }
+int32_t smt_abi_version(void) { return 2; }
 
 const char* smt_status_string(smt_status_t st) {
     switch (st) {
@@ -111,7 +111,8 @@ smt_status_t smt_create(int32_t device, void* stream, smt_ctx** out) {
         c->sm_count = prop.multiProcessorCount;
         c->l2_bytes = (size_t)prop.l2CacheSize;
     }
-    if (cudaMalloc(&c->d_lut, 320 * sizeof(float)) != cudaSuccess ||
+    if (cudaMalloc(&c->d_lut, 320 * sizeof(float)) != cudaSuccess || cudaMalloc(&c->d_flags, 16 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(c->d_flags, 0, 16 * sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&c->h_pinned, 64 * sizeof(int32_t)) != cudaSuccess) {
         smt_destroy(c);
         return SMT_ERR_OOM;
@@ -130,10 +131,34 @@ void smt_destroy(smt_ctx* ctx) {
     }
     for (auto& b : ctx->pool) cudaFree(b.p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->d_redo) cudaFree(ctx->d_redo);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+}  // extern "C"
+
+int* smt_redo_state(smt_ctx* ctx, size_t ntasks) {
+    if (!ctx->d_redo || ctx->d_redo_cap < ntasks) {
+        if (ctx->d_redo) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->d_redo);
+            ctx->d_redo = nullptr;
+        }
+        const size_t cap = ntasks + ntasks / 2 + 1024;
+        if (cudaMalloc(&ctx->d_redo, (FX_ST_LIST + cap) * sizeof(int)) != cudaSuccess) {
+            ctx->d_redo_cap = 0;
+            return nullptr;
+        }
+        cudaMemsetAsync(ctx->d_redo, 0, FX_ST_LIST * sizeof(int), ctx->stream);
+        ctx->d_redo_cap = cap;
+    }
+    return ctx->d_redo;
+}
+
+extern "C" {
 
 smt_status_t smt_sync(smt_ctx* ctx) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
@@ -188,11 +213,13 @@ smt_status_t smt_trim(smt_ctx* ctx) {
 
 smt_status_t smt_device_alloc(smt_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return SMT_ERR_INVALID_ARG;
+    DeviceGuard dg(ctx->device);
     SMT_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
     return SMT_OK;
 }
 smt_status_t smt_device_free(smt_ctx* ctx, void* p) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
+    DeviceGuard dg(ctx->device);
     SMT_CUDA(ctx, cudaFree(p));
     return SMT_OK;
 }

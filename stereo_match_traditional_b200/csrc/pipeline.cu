@@ -5,8 +5,6 @@
 //   first-minimum WTA of the aggregated right volume           (CrossArm.cpp:33; main.cpp:84)
 //   LeftRightConsistency, RemoveSpeckles, MedianFilter         (PostProcessing.h:72,250,314; main.cpp:92-94)
 // Everything stays on the device; only the two image pairs go in and disparity maps come out.
-#include <cstdlib>
-
 #include "common.cuh"
 
 extern "C" void smt_adcensus_default_params(smt_adcensus_params* p, int32_t rows, int32_t cols, int32_t D) {
@@ -42,7 +40,7 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
                 "smt_pipeline_adcensus_full: rows, cols, D must be positive");
     SMT_REQUIRE(ctx, p->sum_mode != SMT_SUM_FAST || p->L1 <= 34, SMT_ERR_UNSUPPORTED,
                 "smt_pipeline_adcensus_full: SMT_SUM_FAST tiles assume arms <= 34 (L1 <= 34, the reference default)");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)H * W, nvol = npix * D;
 
     Marshal ms(ctx, space);
@@ -103,18 +101,9 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     // ---- right view: cost -> aggregate -> WTA
     float* res = nullptr;
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 1, volA.as<float>(), nullptr, nullptr));
-    // Reducing to the disparity inside the last aggregation pass (k_aggregate_cross's wta_disp) saves one write and one
-    // read of the volume but adds a warp reduction per position to a kernel that is not memory-bound: measured 13.71 ms
-    // against 13.05 + 0.45 ms at 1080p x 256, so the separate streaming WTA stays the default (SMT_PIPE_FUSE_WTA=1 switches).
-    static const bool fuse_wta = getenv("SMT_PIPE_FUSE_WTA") != nullptr;
-    if (fuse_wta) {
-        SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
-                                  2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res, dispR.as<float>()));
-    } else {
-        SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
-                                  2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res));
-        SMT_TRY(k_wta(ctx, res, H, W, D, dispR.as<float>()));
-    }
+    // the right view's only consumer is a winner-take-all: the last aggregation pass reduces in the kernel
+    SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
+                              2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res, dispR.as<float>()));
 
     // ---- left view: cost -> aggregate -> 4-path scanline with fused WTA
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 0, volA.as<float>(), nullptr, nullptr));

@@ -362,15 +362,20 @@ struct FillDirs {
     float sina[2][8], cosa[2][8];
 };
 
-__global__ void __launch_bounds__(256) fill_scan_kernel(const int* __restrict__ trg, int ntrg, int width, int height,
-                                                        int* __restrict__ first, int* __restrict__ owner, int* __restrict__ bad) {
+// every (y, x) of a caller-supplied list must address the frame: checked before anything reads or writes through it
+__global__ void __launch_bounds__(256) fill_validate_kernel(const int* __restrict__ trg, int ntrg, int width, int height,
+                                                            int* __restrict__ bad) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= ntrg) return;
     const int y = trg[2 * n], x = trg[2 * n + 1];
-    if (y < 0 || y >= height || x < 0 || x >= width) {
-        *bad = 1;
-        return;
-    }
+    if (y < 0 || y >= height || x < 0 || x >= width) *bad = 1;
+}
+
+__global__ void __launch_bounds__(256) fill_scan_kernel(const int* __restrict__ trg, int ntrg, int width, int height,
+                                                        int* __restrict__ first, int* __restrict__ owner) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ntrg) return;
+    const int y = trg[2 * n], x = trg[2 * n + 1];
     if (y == height / 2) atomicMin(first, n);
     atomicMax(&owner[(size_t)y * width + x], n);
 }
@@ -461,6 +466,15 @@ smt_status_t k_fill_the_hole(smt_ctx* ctx, float* disp, int row, int col, int di
     SMT_CUDA(ctx, cudaMemsetAsync(owner.p, 0xff, n * sizeof(int), ctx->stream));
     SMT_CUDA(ctx, cudaMemsetAsync(st.p, 0, 4 * sizeof(int), ctx->stream));
     int n_mis = *n_mis_inout;
+    // out-of-frame entries (in the as-written variant the axes are swapped, so an ordinary LeftRightConsistency list of a
+    // frame with rows > cols has them) are refused before the map is touched
+    if (n_occ > 0) SMT_LAUNCH(ctx, fill_validate_kernel, cdiv(n_occ, 256), 256, 0, occ, n_occ, width, height, bad);
+    if (n_mis > 0) SMT_LAUNCH(ctx, fill_validate_kernel, cdiv(n_mis, 256), 256, 0, mis, n_mis, width, height, bad);
+    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned[0])
+        return smt_fail(ctx, SMT_ERR_INVALID_ARG,
+                        "smt_fill_the_hole: list entry outside the frame (as written: y < col, x < row, PostProcessing.h:158-159)");
     for (int k = 0; k < 3; ++k) {
         const int32_t* trg = k == 0 ? occ : mis;
         int ntrg = k == 0 ? n_occ : n_mis;
@@ -483,16 +497,11 @@ smt_status_t k_fill_the_hole(smt_ctx* ctx, float* disp, int row, int col, int di
         const int nbt = (int)cdiv(ntrg, 256);
         const int init_first = 0x7fffffff;
         SMT_CUDA(ctx, cudaMemcpyAsync(first, &init_first, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        SMT_LAUNCH(ctx, fill_scan_kernel, nbt, 256, 0, trg, ntrg, width, height, first, owner.as<int>(), bad);
+        SMT_LAUNCH(ctx, fill_scan_kernel, nbt, 256, 0, trg, ntrg, width, height, first, owner.as<int>());
         SMT_LAUNCH(ctx, fill_collect_kernel, nbt, 256, 0, disp, trg, ntrg, width, height, disp_range, k, invalid, dirs, first, switched,
                    fill.as<float>());
         SMT_LAUNCH(ctx, fill_write_kernel, nbt, 256, 0, disp, trg, ntrg, width, fill.as<float>(), owner.as<int>(), first, switched);
     }
-    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_pinned[0])
-        return smt_fail(ctx, SMT_ERR_INVALID_ARG,
-                        "smt_fill_the_hole: list entry outside the frame (as written: y < col, x < row, PostProcessing.h:158-159)");
     *n_mis_inout = n_mis;
     return SMT_OK;
 }
@@ -501,7 +510,7 @@ smt_status_t k_fill_the_hole(smt_ctx* ctx, float* disp, int row, int col, int di
 static smt_status_t lrcheck_common(smt_ctx* ctx, float* dl_inout, const float* dl_const, const float* dr, float* last, int cols,
                                    int rows, float gate, bool variant_and, int32_t* occ, int32_t* n_occ, int32_t* mis,
                                    int32_t* n_mis, smt_memspace_t space) {
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols;
     Marshal ms(ctx, space);
     float* dl = nullptr;
@@ -545,7 +554,7 @@ smt_status_t smt_remove_speckles(smt_ctx* ctx, float* disp, int32_t cols, int32_
                                  int32_t invalid_val, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, disp && cols > 0 && rows > 0, SMT_ERR_INVALID_ARG, "smt_remove_speckles: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     Marshal ms(ctx, space);
     float* d = ms.out(disp, (size_t)rows * cols, true);
     SMT_TRY(ms.check());
@@ -559,7 +568,7 @@ smt_status_t smt_fill_the_hole(smt_ctx* ctx, float* disp, int32_t row, int32_t c
     SMT_REQUIRE(ctx, disp && row > 0 && col > 0 && n_occ >= 0 && n_mis && *n_mis >= 0 && (occ || n_occ == 0) && mis &&
                          (variant == SMT_FILL_AS_WRITTEN || variant == SMT_FILL_FIXED),
                 SMT_ERR_INVALID_ARG, "smt_fill_the_hole: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)row * col;
     SMT_REQUIRE(ctx, (size_t)n_occ <= n && (size_t)*n_mis <= n, SMT_ERR_INVALID_ARG, "smt_fill_the_hole: list longer than the image");
     Marshal ms(ctx, space);
@@ -577,7 +586,7 @@ smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32_t cols,
                         smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, in && out && cols > 0 && rows > 0, SMT_ERR_INVALID_ARG, "smt_median: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* di = ms.in(in, n);

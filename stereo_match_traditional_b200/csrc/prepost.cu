@@ -67,7 +67,7 @@ extern "C" {
 smt_status_t smt_bgr_to_gray(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int32_t cols, uint8_t* gray, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, bgr && gray && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_bgr_to_gray: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const uint8_t* d = ms.in(bgr, n * 3);
@@ -80,7 +80,7 @@ smt_status_t smt_bgr_to_gray(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int
 smt_status_t smt_replicate_pad(smt_ctx* ctx, const uint8_t* img, int32_t rows, int32_t cols, int32_t pad, uint8_t* out, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, img && out && rows > 0 && cols > 0 && pad >= 0, SMT_ERR_INVALID_ARG, "smt_replicate_pad: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols, np = (size_t)(rows + 2 * pad) * (cols + 2 * pad);
     Marshal ms(ctx, space);
     const uint8_t* d = ms.in(img, n);
@@ -93,7 +93,7 @@ smt_status_t smt_replicate_pad(smt_ctx* ctx, const uint8_t* img, int32_t rows, i
 smt_status_t smt_u8_to_f32(smt_ctx* ctx, const uint8_t* img, size_t count, float* out, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, img && out && count > 0, SMT_ERR_INVALID_ARG, "smt_u8_to_f32: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     Marshal ms(ctx, space);
     const uint8_t* d = ms.in(img, count);
     float* o = ms.out(out, count);
@@ -105,7 +105,7 @@ smt_status_t smt_u8_to_f32(smt_ctx* ctx, const uint8_t* img, size_t count, float
 smt_status_t smt_transform_to_show(smt_ctx* ctx, const float* disp, int32_t rows, int32_t cols, uint8_t* out, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, disp && out && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_transform_to_show: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* d = ms.in(disp, n);
@@ -118,7 +118,7 @@ smt_status_t smt_transform_to_show(smt_ctx* ctx, const float* disp, int32_t rows
 smt_status_t smt_normalize_minmax_u8(smt_ctx* ctx, const float* src, int32_t rows, int32_t cols, uint8_t* out, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, src && out && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_normalize_minmax_u8: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* d = ms.in(src, n);

@@ -331,7 +331,7 @@ smt_status_t smt_ad_cost(smt_ctx* ctx, const uint8_t* left, const uint8_t* right
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, left && right && ad && rows > 0 && cols > 0 && D > 0 && (view == 0 || view == 1), SMT_ERR_INVALID_ARG,
                 "smt_ad_cost: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const uint8_t* dl = ms.in(left, npix);
@@ -356,7 +356,7 @@ smt_status_t smt_arms_gray(smt_ctx* ctx, const uint8_t* img, int32_t channels, i
     SMT_REQUIRE(ctx, variant != 0 || rows <= cols, SMT_ERR_UNSUPPORTED,
                 "smt_arms_gray: CrossArmAggregation's Right pass indexes columns < rows (CrossArm.cpp:265); rows > cols is out of "
                 "bounds in the reference");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const uint8_t* dimg = ms.in(img, npix * channels);
@@ -378,7 +378,7 @@ smt_status_t smt_aggregate_rect(smt_ctx* ctx, const float* vol_in, const int32_t
     SMT_REQUIRE(ctx, variant >= 0 && variant <= 2 && (mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST), SMT_ERR_INVALID_ARG,
                 "smt_aggregate_rect: unknown variant or sum mode");
     SMT_REQUIRE(ctx, vol_in != vol_out, SMT_ERR_INVALID_ARG, "smt_aggregate_rect: in-place aggregation is not supported");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* din = ms.in(vol_in, npix * D);

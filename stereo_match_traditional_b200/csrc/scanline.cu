@@ -293,7 +293,7 @@ extern "C" smt_status_t smt_scanline(smt_ctx* ctx, const float* cost, const floa
                                      float* disp, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, cost && gray && rows > 0 && cols > 0 && D > 0, SMT_ERR_INVALID_ARG, "smt_scanline: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols, nvol = npix * D;
     Marshal ms(ctx, space);
     const float* dc = ms.in(cost, nvol);

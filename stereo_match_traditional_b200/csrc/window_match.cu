@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) ncc_stats_kernel(const uint8_t* __restric
 __global__ void __launch_bounds__(256) ncc_select_kernel(const int* __restrict__ slr, const int* __restrict__ l1,
                                                          const int* __restrict__ l2, const int* __restrict__ r1,
                                                          const int* __restrict__ r2, int H, int W, int w, int D,
-                                                         int* __restrict__ disp) {
+                                                         int* __restrict__ disp, double* __restrict__ costs) {
     const int Ho = H - 2 * w, Wo = W - 2 * w;
     const size_t q = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= (size_t)Ho * Wo) return;
@@ -190,11 +190,13 @@ __global__ void __launch_bounds__(256) ncc_select_kernel(const int* __restrict__
                 const long long sr = r1[(size_t)i * W + j - d], srr = r2[(size_t)i * W + j - d];
                 const double num = (double)(n * (long long)raw - sl * sr);
                 c = num / (sdl * sqrt((double)(n * srr - sr * sr)));
+                if (costs) costs[((size_t)i * W + j) * D + d] = c;  // NaN for a zero-variance window, like the reference's 0/0
                 if (c != c) {
                     isnan_c = true;
                     c = -INFINITY;  // a NaN never compares greater (NCC.h:59) and never raises the maximum
                 }
             }
+            if (costs && raw < 0) costs[((size_t)i * W + j) * D + d] = 255.0;
         }
         if (d0 == 0) nan0 = __shfl_sync(0xffffffffu, (int)isnan_c, 0) != 0;
         // exclusive prefix maximum inside the chunk, seeded with the running maximum
@@ -234,7 +236,7 @@ template <bool RIGHT>
 __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __restrict__ own_img, const uint8_t* __restrict__ oth_img,
                                                               int Hp, int Wp, int wins, int D, int T,
                                                               const float* __restrict__ space, const float* __restrict__ color,
-                                                              float* __restrict__ disp) {
+                                                              float* __restrict__ disp, float* __restrict__ costs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = 2 * wins + 1, kk = k * k;
     const int Wo = Wp - 2 * wins;
@@ -297,6 +299,12 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
             const float* w0 = wo + r * k;
             // pb[i] = other-image pixel of cell i at the current tap column
             int pb[ASW_Q];
+            // The reference accumulates both sums in double (ASW.h:212-255).  float32 accumulators are kept within the
+            // 1e-5 bar by summing each tap row on its own and adding the row totals: <= (k-1) + (k-1) roundings on
+            // positive terms instead of k*k - 1, i.e. a worst-case relative error of 48 * 2^-24 = 2.9e-6 for k = 25.
+            float rw[ASW_Q], rv[ASW_Q];
+#pragma unroll
+            for (int i = 0; i < ASW_Q; ++i) rw[i] = rv[i] = 0.f;
 #pragma unroll
             for (int i = 1; i < ASW_Q; ++i) {
                 // the three values that slide in from the previous columns (clamped: cells outside the range are discarded)
@@ -316,8 +324,8 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
                     const float m1 = __fmul_rn(colr[abs(pb[i] - cb[i]) * 32], spc);
                     const float m2 = __fmul_rn(w0c, m1);
                     const int e = min(abs(pa - pb[i]), T);
-                    sw[i] = __fadd_rn(sw[i], m2);
-                    sv[i] = __fadd_rn(sv[i], __fmul_rn(m2, (float)e));
+                    rw[i] = __fadd_rn(rw[i], m2);
+                    rv[i] = __fadd_rn(rv[i], __fmul_rn(m2, (float)e));
                 }
                 if (RIGHT) {
 #pragma unroll
@@ -327,6 +335,11 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
                     for (int i = ASW_Q - 1; i > 0; --i) pb[i] = pb[i - 1];
                 }
             }
+#pragma unroll
+            for (int i = 0; i < ASW_Q; ++i) {
+                sw[i] = __fadd_rn(sw[i], rw[i]);
+                sv[i] = __fadd_rn(sv[i], rv[i]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < ASW_Q; ++i) {
@@ -334,6 +347,7 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
             const bool valid = d < D && (RIGHT ? (jo + d < Wo - wins - 1) : (jo - d >= 0));
             if (valid) {
                 const float cost = __fdiv_rn(sv[i], sw[i]);
+                if (costs) costs[((size_t)io * Wo + jo) * D + d] = cost;
                 if (cost < bestv) {  // ascending d inside the thread: strict '<' keeps the first minimum
                     bestv = cost;
                     bestd = d;
@@ -341,9 +355,19 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
             }
         }
     }
+
     s_bestv[tid] = bestv;
     s_bestd[tid] = bestd;
     __syncthreads();
+    // invalid disparities repeat the previous cost (ASW.h:371): the valid ones are a prefix d < nv of the range (written
+    // above by threads of this block, visible after the barrier)
+    if (costs && jo < Wo) {
+        const int nv = RIGHT ? max(0, min(D, Wo - wins - 1 - jo)) : min(D, jo + 1);
+        if (nv > 0) {
+            const float lastc = costs[((size_t)io * Wo + jo) * D + nv - 1];
+            for (int d = nv + dl; d < D; d += ASW_TD) costs[((size_t)io * Wo + jo) * D + d] = lastc;
+        }
+    }
     if (dl == 0 && jo < Wo) {
         float bv = INFINITY;
         int bd = 0x7fffffff;
@@ -380,7 +404,7 @@ smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     const int w = winsize + 1;
     SMT_REQUIRE(ctx, left_padded && right_padded && disp && D > 0 && winsize >= 0 && rows_padded > 2 * w && cols_padded > 2 * w,
                 SMT_ERR_INVALID_ARG, "smt_sad: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const int Ho = rows_padded - 2 * w, Wo = cols_padded - 2 * w;
     const size_t np = (size_t)rows_padded * cols_padded, no = (size_t)Ho * Wo;
     Marshal ms(ctx, space);
@@ -405,20 +429,22 @@ smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
 }
 
 smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols, int32_t win_size, int32_t D,
-                     int32_t* disp, smt_memspace_t space) {
+                     int32_t* disp, double* costs, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     const int w = win_size;
     SMT_REQUIRE(ctx, left && right && disp && D > 0 && w >= 0 && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_ncc: bad argument");
     SMT_REQUIRE(ctx, (long long)(2 * w + 1) * (2 * w + 1) * 65025 < 2147483647ll, SMT_ERR_UNSUPPORTED,
                 "smt_ncc: window too large for 32-bit window sums");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t np = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const uint8_t* dl = ms.in(left, np);
     const uint8_t* dr = ms.in(right, np);
     int32_t* dd = ms.out(disp, np);
+    double* dcost = ms.out(costs, np * D);
     SMT_TRY(ms.check());
     SMT_CUDA(ctx, cudaMemsetAsync(dd, 0, np * sizeof(int32_t), ctx->stream));  // borders stay 0 (NCC_main.cpp:20)
+    if (dcost) SMT_CUDA(ctx, cudaMemsetAsync(dcost, 0, np * D * sizeof(double), ctx->stream));  // no window there: no cost
     if (rows > 2 * w && cols > 2 * w) {
         const int Ho = rows - 2 * w, Wo = cols - 2 * w;
         SMT_ALLOC(ctx, stats, 4 * np * sizeof(int));
@@ -434,7 +460,7 @@ smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, in
         {
             StageTimer t(ctx, ST_WTA);
             SMT_LAUNCH(ctx, ncc_select_kernel, cdiv((long long)Ho * Wo, 8), 256, 0, vol.as<int>(), s, s + np, s + 2 * np, s + 3 * np, rows,
-                       cols, w, D, dd);
+                       cols, w, D, dd, dcost);
         }
     }
     return ms.finish();
@@ -442,12 +468,12 @@ smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, in
 
 smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded, int32_t cols_padded,
                      int32_t win_size, int32_t D, double space_sigma, double color_sigma, int32_t T, int32_t right_view, float* disp,
-                     smt_memspace_t space) {
+                     float* costs, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     const int wins = win_size + 1, k = 2 * wins + 1;
     SMT_REQUIRE(ctx, left_padded && right_padded && disp && D > 0 && win_size >= 0 && rows_padded > 2 * wins && cols_padded > 2 * wins,
                 SMT_ERR_INVALID_ARG, "smt_asw: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const int Ho = rows_padded - 2 * wins, Wo = cols_padded - 2 * wins;
     const size_t np = (size_t)rows_padded * cols_padded, no = (size_t)Ho * Wo;
     const size_t smem = sizeof(float) * ((size_t)k * k + 256 * 32 + (size_t)ASW_TX * k * k + ASW_TX * ASW_TD) + sizeof(int) * ASW_TX * ASW_TD +
@@ -457,7 +483,9 @@ smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     const uint8_t* dl = ms.in(left_padded, np);
     const uint8_t* dr = ms.in(right_padded, np);
     float* dd = ms.out(disp, no);
+    float* dcost = ms.out(costs, no * D);
     SMT_TRY(ms.check());
+    if (dcost) SMT_CUDA(ctx, cudaMemsetAsync(dcost, 0, no * D * sizeof(float), ctx->stream));
     // masks evaluated on the host in double like the reference (ASW.h:16-47), used as float weights on the device
     std::vector<float> h((size_t)k * k + 256);
     const int c = (k - 1) / 2;
@@ -477,10 +505,10 @@ smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
         dim3 grid(cdiv(Wo, ASW_TX), Ho);
         if (right_view)
             SMT_LAUNCH(ctx, asw_kernel<true>, grid, ASW_TX * ASW_TD, smem, dr, dl, rows_padded, cols_padded, wins, D, T, masks.as<float>(),
-                       masks.as<float>() + (size_t)k * k, dd);
+                       masks.as<float>() + (size_t)k * k, dd, dcost);
         else
             SMT_LAUNCH(ctx, asw_kernel<false>, grid, ASW_TX * ASW_TD, smem, dl, dr, rows_padded, cols_padded, wins, D, T, masks.as<float>(),
-                       masks.as<float>() + (size_t)k * k, dd);
+                       masks.as<float>() + (size_t)k * k, dd, dcost);
     }
     return ms.finish();
 }
@@ -489,7 +517,7 @@ smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, const floa
                                 smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, disp_left && disp_right && out && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_asw_crosscheck: bad argument");
-    SMT_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
     const size_t n = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* dl = ms.in(disp_left, n);

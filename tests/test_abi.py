@@ -22,7 +22,7 @@ def test_header_and_binding_table_agree():
 def test_library_exports_every_declared_symbol(lib):
     for name in _lib.header_symbols():
         assert hasattr(lib, name), name
-    assert lib.smt_abi_version() == 1
+    assert lib.smt_abi_version() == 2
 
 
 def test_status_strings_and_param_defaults(lib):

@@ -224,8 +224,9 @@ def test_pipeline_degenerate_shapes(engine, oracle, H, W, D):
     for n in names:
         assert np.array_equal(got[n], ref[n], equal_nan=True), n
     fast = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=names, sum_mode=SUM_FAST)
+    bar = 0.999 if H * W >= 1000 else 0.99   # below 1000 pixels one differing pixel is already more than 0.1 %
     for n in ("left_raw", "right_raw"):
-        assert (fast[n] == ref[n]).mean() >= 0.99 and np.abs(fast[n] - ref[n]).max() <= 1, n   # few pixels: 1 % = a handful
+        assert (fast[n] == ref[n]).mean() >= bar and np.abs(fast[n] - ref[n]).max() <= 1, n
 
 
 def test_pipeline_caller_owned_output(engine, oracle):

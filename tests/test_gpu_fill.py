@@ -69,6 +69,26 @@ def test_fill_refuses_entries_outside_its_frame(engine):
         engine.fill_the_hole(d, 8, bad, np.zeros((0, 2), np.int32))
 
 
+def test_fill_as_written_refuses_tall_frame_lists_untouched(engine):
+    """rows > cols: an ordinary LeftRightConsistency list holds y >= cols, which the as-written variant (y < col, x < row,
+    PostProcessing.h:158-159) cannot address.  Also negative entries.  The call must fail with INVALID_ARG before the map
+    is read or written through such an entry, and the context must stay usable."""
+    from stereo_match_traditional_b200.api import SmtError
+
+    rows, cols = 40, 12
+    rng = np.random.default_rng(5)
+    d = rng.integers(0, 8, (rows, cols)).astype(np.float32)
+    occ = np.array([[3, 4], [30, 5]], np.int32)           # y = 30 >= height = cols = 12
+    mis = np.array([[2, 2], [-7, 1]], np.int32)           # negative row
+    for o, m in ((occ, np.zeros((0, 2), np.int32)), (occ[:1], mis)):
+        before = d.copy()
+        with pytest.raises(SmtError):
+            engine.fill_the_hole(d, 8, o, m)
+        assert np.array_equal(d, before)
+    ok, _ = engine.fill_the_hole(d, 8, occ[:1], np.zeros((0, 2), np.int32))   # the context still works
+    assert ok.shape == d.shape
+
+
 @pytest.mark.parametrize("shape", [(48, 80, 16), (80, 48, 24), (120, 200, 32)])
 def test_fill_fixed_variant_after_lrcheck(engine, oracle_port, shape):
     """SMT_FILL_FIXED (axes not swapped, invalid = +inf) fed by the lists and the +inf map of LeftRightConsistency.
