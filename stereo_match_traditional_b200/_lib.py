@@ -12,7 +12,8 @@ import subprocess
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libsmt_b200.so"
+# SMT_B200_LIB: developer override used by scripts/ab_agg.sh to time alternative builds of the same library (A/B runs)
+LIB_PATH = Path(os.environ.get("SMT_B200_LIB") or HERE / "libsmt_b200.so")
 CSRC = HERE / "csrc"
 HEADER = HERE.parent / "include" / "smt_b200.h"
 

@@ -32,8 +32,14 @@ namespace {
 constexpr int FX_CH = 24;     // positions per chunk
 constexpr int FX_R = 72;      // ring slots = 3 chunks (span needed: 71)
 constexpr int FX_LOOK = 35;   // output j is computable once E[j+35] is stored
-constexpr int FX_DLAG = 4;    // descriptor read this many positions ahead of its ring reads
-constexpr int FX_RLAG = 4;    // ring reads consumed this many positions after they are issued
+#ifndef SMT_FX_DLAG
+#define SMT_FX_DLAG 4
+#endif
+#ifndef SMT_FX_RLAG
+#define SMT_FX_RLAG 4
+#endif
+constexpr int FX_DLAG = SMT_FX_DLAG;  // descriptor read this many positions ahead of its ring reads
+constexpr int FX_RLAG = SMT_FX_RLAG;  // ring reads consumed this many positions after they are issued
 constexpr int FX_PLANE = FX_R * 128;  // bytes of one ring plane (72 slots x 32 lanes x 4 B)
 #ifndef SMT_FX_L2PF
 #define SMT_FX_L2PF 2         // chunks between the register loads and the L2 prefetch running ahead of them
@@ -48,13 +54,18 @@ __device__ __forceinline__ float fx_div(float a, float b, float y) {
 
 // window descriptor of one output position: byte offsets of E[j-lo] and E[j+hi+1] in the lane's ring column (the plane
 // of a dividing pass included), and for a dividing pass  bq = count / quantum, yq = RN(1/count) x quantum  (exact
-// quotient, single pass) or  bq = quantum ratio / count  (fused pair: the mean only feeds the next quantisation)
+// quotient)
 struct __align__(16) FxDesc {
     unsigned offa, offb;
     float bq, yq;
 };
-struct __align__(8) FxDescB {
+// the fused pair reads ONE 16-byte record per step: byte offsets of A's window of item k (plane included), A's quantum
+// ratio / count, and the two 16-bit byte offsets of B's window of item k - FX2_S3.  (An 8-byte record with four slot
+// indices, one LDS.64 and byte extraction measured 2.5 % slower: the extra PRMT / IMAD cost more than the narrower load.)
+struct __align__(16) FxRec {
     unsigned offa, offb;
+    float rq;
+    unsigned offs_b;  // B: offa | offb << 16
 };
 
 struct FxPre {  // raw {left,right,top,bottom} arm word and support count of this lane's output position in the NEXT chunk
@@ -292,9 +303,12 @@ __global__ void __launch_bounds__(FX1_WARPS * 32, PRIMED ? 3 : 4)
 // Items with a negative index belong to the previous chunk; their in-flight values cross the chunk boundary in registers
 // (FxCarry).  B's window descriptors were prepared together with A's one or two chunks earlier and wait in a three-chunk
 // descriptor ring.
+#ifndef SMT_FX2_ONEBODY
+#define SMT_FX2_ONEBODY 1
+#endif
 constexpr int FX2_WARPS = 4;
 constexpr int FX2_S3 = FX_RLAG + 1, FX2_S4 = 2 * FX_RLAG + 1;  // stage lags in positions
-constexpr int FX2_SMEM_PER_WARP = 3 * FX_PLANE + 3 * FX_CH * (int)sizeof(FxDescB);
+constexpr int FX2_SMEM_PER_WARP = 3 * FX_PLANE + 3 * FX_CH * (int)sizeof(unsigned);
 
 struct FxCarry {
     unsigned eaA[FX_RLAG], ebA[FX_RLAG];
@@ -308,33 +322,39 @@ __device__ __forceinline__ void fx2_chunk(FxAcc& accA, FxAcc& accB, FxCarry& cy,
                                           float (&vload)[FX_CH], int tb, int tbm, int o3, int len, bool act,
                                           const float* __restrict__ src_next, float* __restrict__ dst_first, long long step_rt,
                                           long long mbase, long long mstride, int horiz, const unsigned* __restrict__ arms,
-                                          const uint16_t* __restrict__ sup, unsigned char* ringA, unsigned char* ringB, FxDesc* descA,
-                                          FxDescB* descB, int lane, float inv_q, float q, unsigned vm1, int zero) {
+                                          const uint16_t* __restrict__ sup, unsigned char* ringA, unsigned char* ringB, FxRec* descA,
+                                          unsigned* descB, int lane, float inv_q, float q, unsigned vm1, int zero) {
     const long long step = CSTEP ? (long long)CSTEP : step_rt;
     const long long step_b = step * 4;
-    // descriptor rows of B: this chunk writes row o3, reads rows (o3+2)%3 (one chunk ago) and (o3+1)%3 (two chunks ago)
-    FxDescB* const dB_w = descB + o3 * FX_CH;
-    const FxDescB* const dB_1 = descB + (o3 == 0 ? 2 : o3 - 1) * FX_CH;
-    const FxDescB* const dB_2 = descB + (o3 == 2 ? 0 : o3 + 1) * FX_CH;
+    // B's window slots wait in a three-chunk ring: this chunk writes row o3, reads rows (o3+2)%3 (one chunk ago) and
+    // (o3+1)%3 (two chunks ago)
+    unsigned* const dB_w = descB + o3 * FX_CH;
+    const unsigned* const dB_1 = descB + (o3 == 0 ? 2 : o3 - 1) * FX_CH;
+    const unsigned* const dB_2 = descB + (o3 == 2 ? 0 : o3 + 1) * FX_CH;
     {
         const int j = tb - FX_LOOK + lane;
-        FxDesc da{0u, 0u, 0.f, 0.f};
-        FxDescB db{0u, 0u};
+        FxRec rec{0u, 0u, 0.f, 0u};
+        unsigned db = 0u;
         if (lane < FX_CH && (!EDGE || (j >= 0 && j < len))) {
             const unsigned aw = horiz ? (pre.armw & 0xffffu) : (pre.armw >> 16);
-            fx_window(j, aw, len, tb, tbm, 0, da.offa, da.offb);
-            fx_window(j, aw, len, tb, tbm, FX_LOOK, db.offa, db.offb);
+            unsigned oa, ob, pa, pb;
+            fx_window(j, aw, len, tb, tbm, 0, oa, ob);
+            fx_window(j, aw, len, tb, tbm, FX_LOOK, pa, pb);
             const bool coarse = pre.cnt >= 128;
-            if (coarse) {
-                da.offa += FX_PLANE;
-                da.offb += FX_PLANE;
-            }
-            da.bq = __fmul_rn(__frcp_rn((float)pre.cnt), coarse ? 64.f : 1.f);  // window sum in its plane's quanta -> mean in quanta
+            const unsigned plane = coarse ? (unsigned)FX_PLANE : 0u;
+            rec.offa = oa + plane;
+            rec.offb = ob + plane;
+            db = pa | (pb << 16);
+            rec.rq = __fmul_rn(__frcp_rn((float)pre.cnt), coarse ? 64.f : 1.f);  // window sum in its plane's quanta -> mean in quanta
         }
         __syncwarp();
+        // one record per step: A's window of item `lane` and B's window of item lane - FX2_S3, prepared one or two chunks
+        // ago: row o-1 at i-11 (i >= 11) or row o-2 at i+13
         if (lane < FX_CH) {
-            descA[lane] = da;
             dB_w[lane] = db;
+            const int i = lane - FX2_S3;
+            rec.offs_b = (i < 11) ? dB_2[i + 13] : dB_1[i - 11];
+            descA[lane] = rec;
         }
         __syncwarp();
     }
@@ -363,8 +383,7 @@ __device__ __forceinline__ void fx2_chunk(FxAcc& accA, FxAcc& accB, FxCarry& cy,
         unsigned eaA[FX_RLAG + FX_CH], ebA[FX_RLAG + FX_CH];  // item i at [i + RLAG]
         float rq[FX_RLAG + FX_CH];
         unsigned eaB[FX_RLAG + FX_CH], ebB[FX_RLAG + FX_CH];  // item i at [i + FX2_S4]
-        FxDesc dA[FX_CH];                                     // item k at [k]
-        FxDescB dB[FX_CH];                                    // item k - FX2_S3 at [k]
+        FxRec dA[FX_CH];                                      // step k: A's item k, B's item k - FX2_S3
 #pragma unroll
         for (int u = 0; u < FX_RLAG; ++u) {
             eaA[u] = cy.eaA[u];
@@ -374,13 +393,8 @@ __device__ __forceinline__ void fx2_chunk(FxAcc& accA, FxAcc& accB, FxCarry& cy,
             ebB[u] = cy.ebB[u];
         }
         unsigned tqb = cy.tqb;
-        // B's descriptor of item i (output tb+i-70) sits in row o-1 at i-11 (i >= 11) or in row o-2 at i+13
-#define SMT_FX2_DB(i) (((i) < 11) ? dB_2[(i) + 13] : dB_1[(i)-11])
 #pragma unroll
-        for (int u = 0; u < FX_DLAG; ++u) {
-            dA[u] = descA[u];
-            dB[u] = SMT_FX2_DB(u - FX2_S3);
-        }
+        for (int u = 0; u < FX_DLAG; ++u) dA[u] = descA[u];
 #pragma unroll
         for (int k = 0; k < FX_CH; ++k) {
             // ---- the shared-memory traffic of the iteration first: none of it waits for this iteration's arithmetic
@@ -391,13 +405,10 @@ __device__ __forceinline__ void fx2_chunk(FxAcc& accA, FxAcc& accB, FxCarry& cy,
             }
             eaA[FX_RLAG + k] = *reinterpret_cast<const unsigned*>(ringA + dA[k].offa);
             ebA[FX_RLAG + k] = *reinterpret_cast<const unsigned*>(ringA + dA[k].offb);
-            rq[FX_RLAG + k] = dA[k].bq;
-            eaB[FX_RLAG + k] = *reinterpret_cast<const unsigned*>(ringB + dB[k].offa);
-            ebB[FX_RLAG + k] = *reinterpret_cast<const unsigned*>(ringB + dB[k].offb);
-            if (k + FX_DLAG < FX_CH) {
-                dA[k + FX_DLAG] = descA[k + FX_DLAG];
-                dB[k + FX_DLAG] = SMT_FX2_DB(k + FX_DLAG - FX2_S3);
-            }
+            rq[FX_RLAG + k] = dA[k].rq;
+            eaB[FX_RLAG + k] = *reinterpret_cast<const unsigned*>(ringB + (dA[k].offs_b & 0xffffu));
+            ebB[FX_RLAG + k] = *reinterpret_cast<const unsigned*>(ringB + (dA[k].offs_b >> 16));
+            if (k + FX_DLAG < FX_CH) dA[k + FX_DLAG] = descA[k + FX_DLAG];
             // ---- S2: A's output of item k - RLAG
             {
                 const float mean_q = __fmul_rn(__uint2float_rn(ebA[k] - eaA[k]), rq[k]);
@@ -412,7 +423,6 @@ __device__ __forceinline__ void fx2_chunk(FxAcc& accA, FxAcc& accB, FxCarry& cy,
                 dp += step_b;
             }
         }
-#undef SMT_FX2_DB
 #pragma unroll
         for (int u = 0; u < FX_RLAG; ++u) {
             cy.eaA[u] = eaA[FX_CH + u];
@@ -431,14 +441,14 @@ __global__ void __launch_bounds__(FX2_WARPS * 32, 2)
                    const uint16_t* __restrict__ sup, int H, int W, int D, int horiz, int tmaps, float inv_q, float q, unsigned vm1,
                    int* __restrict__ state, int zero) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ FxDesc s_descA_all[FX2_WARPS][FX_CH];
+    __shared__ FxRec s_descA_all[FX2_WARPS][FX_CH];
     if (*reinterpret_cast<volatile int*>(state + FX_ST_ESCALATED) != 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = smem_raw + (size_t)warp * FX2_SMEM_PER_WARP;
     unsigned char* ringA = base + lane * 4;                 // two planes
     unsigned char* ringB = base + 2 * FX_PLANE + lane * 4;  // one plane
-    FxDescB* descB = reinterpret_cast<FxDescB*>(base + 3 * FX_PLANE);
-    FxDesc* descA = s_descA_all[warp];
+    unsigned* descB = reinterpret_cast<unsigned*>(base + 3 * FX_PLANE);
+    FxRec* descA = s_descA_all[warp];
     const int nchunk = (D + 31) >> 5;
     const long long wg = (long long)blockIdx.x * FX2_WARPS + warp;
     const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(FX2_WARPS * 32, 2)
 
     // B's outputs of the first chunks lie before the line: their descriptors must read as "empty window"; slot 0 of both
     // rings is read through empty descriptors before anything is stored there
-    for (int k = lane; k < 3 * FX_CH; k += 32) descB[k] = FxDescB{0u, 0u};
+    for (int k = lane; k < 3 * FX_CH; k += 32) descB[k] = 0;
     *reinterpret_cast<unsigned*>(ringA) = 0u;
     *reinterpret_cast<unsigned*>(ringB) = 0u;
     __syncwarp();
@@ -492,10 +502,20 @@ __global__ void __launch_bounds__(FX2_WARPS * 32, 2)
         o3 = o3 == 2 ? 0 : o3 + 1;                                                                                            \
         ++o;                                                                                                                  \
     }
+#if SMT_FX2_ONEBODY
+    // one copy of the chunk body instead of two with the buffers swapped: 24 register moves per chunk buy half the code
+    // (the body is ~1000 instructions and only two warps share a scheduler's instruction cache)
+    for (int o = 0; o < nouter;) {
+        SMT_FX2_STEP(va, vb)
+#pragma unroll
+        for (int k = 0; k < FX_CH; ++k) va[k] = vb[k];
+    }
+#else
     for (int o = 0; o < nouter;) {
         SMT_FX2_STEP(va, vb)
         SMT_FX2_STEP(vb, va)
     }
+#endif
 #undef SMT_FX2_STEP
     if (__any_sync(0xffffffffu, bad != 0u) && lane == 0) fx_request_redo(state, (int)wg);
 }
