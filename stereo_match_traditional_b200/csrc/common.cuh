@@ -26,6 +26,10 @@ struct smt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // side stream of the pipeline entry points: image-sized, latency-bound kernels (arm construction) run on it beside
+    // the volume-sized kernels of the main stream; created on first use
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_side[2] = {nullptr, nullptr};
     std::string last_error;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -73,6 +77,18 @@ struct DeviceGuard {
     }
     DeviceGuard(const DeviceGuard&) = delete;
     DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// Runs the enclosed launches on the context's side stream: fork() makes the side stream wait for everything queued on
+// the main stream so far; the destructor switches back; join(k) makes the main stream wait for side-stream event k.
+struct SideStream {
+    smt_ctx* ctx;
+    cudaStream_t main;
+    bool ok = false;
+    explicit SideStream(smt_ctx* c);
+    ~SideStream() { ctx->stream = main; }
+    void mark(int k) { if (ok) cudaEventRecord(ctx->ev_side[k], ctx->side); }
+    static void join(smt_ctx* c, int k) { if (c->side) cudaStreamWaitEvent(c->stream, c->ev_side[k], 0); }
 };
 
 // RAII device buffer from the context's pool.
@@ -221,7 +237,7 @@ smt_status_t k_adcensus_cost(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, c
                              int view, float* cost, float* ad, float* census);
 smt_status_t k_wta(smt_ctx* ctx, const float* vol, int H, int W, int D, float* disp);
 smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1, int L2, int t1, int t2, uint8_t* arms,
-                          uint16_t* sup0, uint16_t* sup1);
+                          uint16_t* sup0, uint16_t* sup1, uint32_t* scratch = nullptr);
 // aggregates `vol` (modified: ping-pongs between vol and tmp); *result points at whichever buffer holds the answer
 smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
                                const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result,

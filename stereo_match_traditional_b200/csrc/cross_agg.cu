@@ -129,15 +129,18 @@ __global__ void __launch_bounds__(128) support_count_kernel(const uchar4* __rest
     if (sup1) sup1[(size_t)y * W + x] = (uint16_t)c1;
 }
 
+// scratch (optional): rows*cols uint32 owned by the caller -- needed when the call runs on a stream other than the one
+// later pool allocations are used on (the pool recycles a block as soon as the host-side owner lets go of it)
 smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1, int L2, int t1, int t2, uint8_t* arms,
-                          uint16_t* sup0, uint16_t* sup1) {
+                          uint16_t* sup0, uint16_t* sup1, uint32_t* scratch) {
     StageTimer t(ctx, ST_ARMS);
     dim3 grid(cdiv(W, 128), H);
     if (t1 >= 1 && t1 <= 128 && t2 >= 1 && t2 <= 128) {
         const size_t npix = (size_t)H * W;
-        SMT_ALLOC(ctx, packed, npix * sizeof(uint32_t));
-        SMT_LAUNCH(ctx, pack_bgr_kernel, cdiv((long long)npix, 256), 256, 0, bgr, npix, packed.as<uint32_t>());
-        SMT_LAUNCH(ctx, cross_arms_packed_kernel, grid, 128, 0, packed.as<uint32_t>(), H, W, L1, L2, (unsigned)(128 - t1) * 0x01010101u,
+        SMT_ALLOC(ctx, own, scratch ? 0 : npix * sizeof(uint32_t));
+        uint32_t* packed = scratch ? scratch : own.as<uint32_t>();
+        SMT_LAUNCH(ctx, pack_bgr_kernel, cdiv((long long)npix, 256), 256, 0, bgr, npix, packed);
+        SMT_LAUNCH(ctx, cross_arms_packed_kernel, grid, 128, 0, packed, H, W, L1, L2, (unsigned)(128 - t1) * 0x01010101u,
                    (unsigned)(128 - t2) * 0x01010101u, reinterpret_cast<uchar4*>(arms));
     } else {
         SMT_LAUNCH(ctx, cross_arms_kernel, grid, 128, 0, bgr, H, W, L1, L2, t1, t2, reinterpret_cast<uchar4*>(arms));

@@ -70,6 +70,19 @@ StageTimer::~StageTimer() {
     if (idx >= 0) cudaEventRecord(ctx->pending[idx].b, ctx->stream);
 }
 
+SideStream::SideStream(smt_ctx* c) : ctx(c), main(c->stream) {
+    if (!ctx->side) {
+        if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) { ctx->side = nullptr; return; }
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_side[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_side[1], cudaEventDisableTiming);
+    }
+    cudaEventRecord(ctx->ev_fork, main);
+    cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+    ctx->stream = ctx->side;
+    ok = true;
+}
+
 extern "C" {
 
 int32_t smt_abi_version(void) { return 2; }
@@ -134,6 +147,13 @@ void smt_destroy(smt_ctx* ctx) {
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->d_redo) cudaFree(ctx->d_redo);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->side) {
+        cudaStreamSynchronize(ctx->side);
+        cudaStreamDestroy(ctx->side);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_side[0]);
+        cudaEventDestroy(ctx->ev_side[1]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

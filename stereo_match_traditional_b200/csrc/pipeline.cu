@@ -64,6 +64,7 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     SMT_ALLOC(ctx, maps, census_maps_bytes(H, W));
     SMT_ALLOC(ctx, armsL, npix * 8);
     SMT_ALLOC(ctx, armsR, npix * 8);
+    SMT_ALLOC(ctx, arms_scratch, 2 * npix * sizeof(uint32_t));
     SMT_ALLOC(ctx, dispL, npix * sizeof(float));
     SMT_ALLOC(ctx, dispR, npix * sizeof(float));
     SMT_ALLOC(ctx, counts, 2 * sizeof(int));
@@ -82,9 +83,6 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     SMT_TRY(k_u8_to_f32(ctx, gl, npix, grayf.as<float>()));
     SMT_TRY(k_ensure_lut(ctx, p->sigmaC, p->sigmaS));
 
-    CensusMaps cm;
-    census_maps_carve(maps.p, H, W, &cm);
-    SMT_TRY(k_census_maps(ctx, gl, gr, H, W, cm));
 
     auto arms_of = [&](DevBuf& b, uint8_t** arms, uint16_t** s0, uint16_t** s1) {
         *arms = b.as<uint8_t>();
@@ -95,18 +93,37 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     uint16_t *s0L, *s1L, *s0R, *s1R;
     arms_of(armsL, &aL, &s0L, &s1L);
     arms_of(armsR, &aR, &s0R, &s1R);
-    SMT_TRY(k_cross_arms(ctx, bl, H, W, p->L1, p->L2, p->t1, p->t2, aL, s0L, s1L));
-    SMT_TRY(k_cross_arms(ctx, br, H, W, p->L1, p->L2, p->t1, p->t2, aR, s0R, s1R));
+    // arm construction is image-sized and latency-bound: it runs on the side stream beside the census maps and the cost
+    // kernels (right view first: its aggregation comes first); stage timing keeps everything on one stream
+    const bool overlap = !ctx->timing;
+    if (overlap) {
+        SideStream side(ctx);
+        smt_status_t st = k_cross_arms(ctx, br, H, W, p->L1, p->L2, p->t1, p->t2, aR, s0R, s1R, arms_scratch.as<uint32_t>());
+        side.mark(0);
+        if (st == SMT_OK) st = k_cross_arms(ctx, bl, H, W, p->L1, p->L2, p->t1, p->t2, aL, s0L, s1L, arms_scratch.as<uint32_t>() + npix);
+        side.mark(1);
+        if (st != SMT_OK) return st;
+    }
+
+    CensusMaps cm;
+    census_maps_carve(maps.p, H, W, &cm);
+    SMT_TRY(k_census_maps(ctx, gl, gr, H, W, cm));
+    if (!overlap) {
+        SMT_TRY(k_cross_arms(ctx, br, H, W, p->L1, p->L2, p->t1, p->t2, aR, s0R, s1R));
+        SMT_TRY(k_cross_arms(ctx, bl, H, W, p->L1, p->L2, p->t1, p->t2, aL, s0L, s1L));
+    }
 
     // ---- right view: cost -> aggregate -> WTA
     float* res = nullptr;
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 1, volA.as<float>(), nullptr, nullptr));
+    if (overlap) SideStream::join(ctx, 0);
     // the right view's only consumer is a winner-take-all: the last aggregation pass reduces in the kernel
     SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aR, s0R, s1R, H, W, D, p->agg_iters, p->sum_mode,
                               2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res, dispR.as<float>()));
 
     // ---- left view: cost -> aggregate -> 4-path scanline with fused WTA
     SMT_TRY(k_adcensus_cost(ctx, gl, gr, cm, H, W, D, 0, volA.as<float>(), nullptr, nullptr));
+    if (overlap) SideStream::join(ctx, 1);
     SMT_TRY(k_aggregate_cross(ctx, volA.as<float>(), volB.as<float>(), aL, s0L, s1L, H, W, D, p->agg_iters, p->sum_mode, 2.0f /* AD-Census cost < 2 (AD-Census.h:287-289) */, &res));
     float* scratch = (res == volA.as<float>()) ? volB.as<float>() : volA.as<float>();
     SMT_TRY(k_scanline(ctx, res, grayf.as<float>(), H, W, D, p->p1, p->p2, nullptr, nullptr, nullptr, nullptr, nullptr,
