@@ -138,6 +138,46 @@ SMT_API smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int3
                                                const uint16_t* sup_vfirst, int32_t rows, int32_t cols, int32_t D,
                                                float vmax, smt_sum_mode_t mode, smt_memspace_t space);
 
+/* ------------------------------------------------------------------------------------------------ row-band split
+ * One very large frame split into row bands over several GPUs, for the cost and cross-aggregation stages
+ * (BASELINE.json configs[4]; the reference has no counterpart: CrossAggregator::Aggregate, CBLSM/cross_aggregator.cpp:89-118,
+ * runs on the whole frame and its `int` indices overflow at 7680x4320x512).  Rank g of `world` owns rows
+ * [g*ceil(rows/world), ...) and keeps a 34-row halo (the maximum arm length) beyond each interior edge.
+ *   smt_band_create      allocates the band: two volumes float32 [top + owned + bottom][cols][D] plus a small header
+ *   smt_band_geometry    owned image rows [r0, r1) and halo heights
+ *   smt_band_volume      device pointer of volume 0: the caller writes the initial cost of its OWNED rows at row `top`
+ *                        (e.g. smt_ad_cost on those image rows) and finds the aggregated cost there afterwards
+ *   smt_band_export / smt_band_connect        neighbours in OTHER processes (one process per GPU): exchange the 128-byte
+ *                        handles by any host channel, then map the upper / lower neighbour (CUDA IPC, peer access)
+ *   smt_band_connect_local                    neighbours in THIS process (contexts on the same or on peer devices)
+ *   smt_halo_exchange    one-sided exchange for volume 0: copies the 34 top / bottom owned rows into the neighbours' halo
+ *                        rows over NVLink, stores a sequence number in their headers, and queues this context's stream
+ *                        behind the neighbours' numbers (a spinning one-warp kernel: no host synchronisation, no collective)
+ *   smt_band_aggregate_cross   CrossAggregator::Aggregate(iters) on the band: horizontal passes on the owned rows, one
+ *                        exchange before every vertical pass (overlapped with the interior rows of the horizontal pass in
+ *                        front of it); arms / sup_*: the band's rows [r0-top, r1+bottom) of the FULL image's maps
+ *                        (smt_cross_arms on the whole image, sliced).  SMT_SUM_REFERENCE_ORDER: bit-identical to the whole
+ *                        frame and to the reference; SMT_SUM_FAST: within the usual 1e-5, arms <= 34
+ *   smt_band_sync        waits for the band's streams; SMT_ERR_CUDA if an exchange timed out; bytes pushed so far
+ * All ranks must call smt_band_aggregate_cross with the same iters; calls are asynchronous on the context's stream. */
+typedef struct smt_band smt_band;
+#define SMT_BAND_HANDLE_BYTES 128
+typedef struct smt_band_handle {
+    unsigned char bytes[SMT_BAND_HANDLE_BYTES];
+} smt_band_handle;
+SMT_API smt_status_t smt_band_create(smt_ctx* ctx, int32_t image_rows, int32_t cols, int32_t D, int32_t rank, int32_t world,
+                                     smt_band** out);
+SMT_API void smt_band_destroy(smt_band* band);
+SMT_API smt_status_t smt_band_geometry(const smt_band* band, int32_t* r0, int32_t* r1, int32_t* top, int32_t* bottom);
+SMT_API smt_status_t smt_band_volume(smt_band* band, float** vol);
+SMT_API smt_status_t smt_band_export(smt_band* band, smt_band_handle* out);
+SMT_API smt_status_t smt_band_connect(smt_band* band, const smt_band_handle* upper, const smt_band_handle* lower);
+SMT_API smt_status_t smt_band_connect_local(smt_band* band, smt_band* upper, smt_band* lower);
+SMT_API smt_status_t smt_halo_exchange(smt_band* band);
+SMT_API smt_status_t smt_band_aggregate_cross(smt_band* band, const uint8_t* arms, const uint16_t* sup_hfirst,
+                                              const uint16_t* sup_vfirst, int32_t iters, float vmax, smt_sum_mode_t mode);
+SMT_API smt_status_t smt_band_sync(smt_band* band, double* pushed_bytes);
+
 /* SMT_SUM_FAST evaluates window sums as differences of 32-bit wrap-around fixed-point prefixes (quantum = 2^-25 of the
  * power of two above the largest cost).  That is accurate to 2^-20 per pass as long as every non-zero value entering a
  * window is at least 2^19 quanta; lines that hold a smaller value are redone on compensated float32-pair prefixes, and

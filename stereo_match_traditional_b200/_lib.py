@@ -76,6 +76,16 @@ SIGNATURES = {
     "smt_cross_sweep_info": (_i, [_i, _i, _i32p, _i32p]),
     "smt_aggregate_cross_sweep": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i]),
     "smt_aggregate_fast_status": (_i, [_vp, _i32p]),
+    "smt_band_create": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "smt_band_destroy": (None, [_vp]),
+    "smt_band_geometry": (_i, [_vp, _i32p, _i32p, _i32p, _i32p]),
+    "smt_band_volume": (_i, [_vp, C.POINTER(_vp)]),
+    "smt_band_export": (_i, [_vp, _vp]),
+    "smt_band_connect": (_i, [_vp, _vp, _vp]),
+    "smt_band_connect_local": (_i, [_vp, _vp, _vp]),
+    "smt_halo_exchange": (_i, [_vp]),
+    "smt_band_aggregate_cross": (_i, [_vp, _vp, _vp, _vp, _i, _f, _i]),
+    "smt_band_sync": (_i, [_vp, _f64p]),
     "smt_ad_cost": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
     "smt_arms_gray": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i32p, _i]),
     "smt_aggregate_rect": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),

@@ -181,6 +181,22 @@ class Engine:
             self._torch_stream = torch.cuda.ExternalStream(int(self._raw.smt_get_stream(self.h)), device=f"cuda:{self.device}")
         return self._torch_stream
 
+    def order_after_torch(self):
+        """Queue the context's stream behind the work torch's current stream already holds."""
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.torch_stream.cuda_stream:
+            self.torch_stream.wait_stream(cur)
+
+    def order_torch_after(self):
+        """Make torch's current stream wait for what the context's stream holds."""
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.torch_stream.cuda_stream:
+            cur.wait_stream(self.torch_stream)
+
     def trim(self):
         self._ck(self.lib.smt_trim(self.h))
 

@@ -242,6 +242,26 @@ smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1
 smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms, const uint16_t* sup0,
                                const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result,
                                float* wta_disp = nullptr);
+// ---- cross aggregation building blocks (cross_agg*.cu).  st_lo, st_hi: only outputs at positions [st_lo, st_hi) of each
+// walked line are stored (st_hi <= 0: the whole line); redo: the FX_ST_* state of the fixed-point sweep queued in front
+bool fx_quantum(float vmax, float* inv_q, float* q);
+smt_status_t k_fx_state_reset(smt_ctx* ctx, int* state, bool new_aggregation, size_t ntasks);
+smt_status_t k_agg_fx_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
+                           int horiz, int tmaps, float inv_q, float q, int* state, int st_lo = 0, int st_hi = 0);
+smt_status_t k_agg_fx_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
+                           int horiz, int tmaps, float inv_q, float q, int* state);
+smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
+                            int horiz, bool nonneg, float bias, int tmaps, const int* redo, int st_lo = 0, int st_hi = 0);
+smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const uint8_t* arms8, const uint16_t* s, int H, int W, int D,
+                              int horiz, int st_lo = 0, int st_hi = 0);
+smt_status_t k_transpose_maps(smt_ctx* ctx, const uint8_t* arms8, const uint16_t* sup, int H, int W, uint8_t* armsT, uint16_t* supT);
+smt_status_t k_arms_max(smt_ctx* ctx, const uint8_t* arms8, size_t npix, int* longest);  // synchronises
+// one of the 2*iters one-dimensional passes of CrossAggregator::Aggregate on a volume of `rows` rows (the per-sweep ABI and
+// the row-band split are built on it); first_of_aggregation resets the redo state of the fast mode; ntasks_whole: (line,
+// chunk) tasks of the largest pass of the aggregation when this call only covers part of a volume (sizes the redo list)
+smt_status_t k_cross_sweep(smt_ctx* ctx, int iters, int sweep, const float* vol_in, float* vol_out, const uint8_t* arms,
+                           const uint16_t* sup_hfirst, const uint16_t* sup_vfirst, int rows, int cols, int D, float vmax,
+                           smt_sum_mode_t mode, bool first_of_aggregation, int st_lo = 0, int st_hi = 0, size_t ntasks_whole = 0);
 smt_status_t k_scanline(smt_ctx* ctx, const float* cost, const float* gray, int H, int W, int D, int p1, int p2,
                         float* left, float* right, float* up, float* down, float* sum, float* disp, float* scratch_a,
                         float* scratch_b);

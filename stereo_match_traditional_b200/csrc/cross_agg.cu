@@ -156,15 +156,16 @@ smt_status_t k_cross_arms(smt_ctx* ctx, const uint8_t* bgr, int H, int W, int L1
 template <bool HORIZ>
 __global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                              const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
-                                                             int H, int W, int D) {
+                                                             int H, int W, int D, int st_lo, int st_hi) {
     const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t ncell = (size_t)H * W * D;
     if (cell >= ncell) return;
     const size_t pix = cell / D;
     const int d = (int)(cell - pix * D);
     const uchar4 a = arms[pix];
-    // arms stop at the image border; the clamps only act on the halo rows of a row band, whose results are never used
+    // arms stop at the image border; the clamps only act on the halo rows of a row band, whose results are never stored
     const int pos = HORIZ ? (int)(pix % W) : (int)(pix / W), len = HORIZ ? W : H;
+    if (pos < st_lo || pos >= st_hi) return;
     const int lo = -min(HORIZ ? (int)a.x : (int)a.z, pos);
     const int hi = min(HORIZ ? (int)a.y : (int)a.w, len - 1 - pos);
     const long long step = HORIZ ? (long long)D : (long long)W * D;
@@ -178,41 +179,6 @@ __global__ void __launch_bounds__(256) agg_pass_exact_kernel(const float* __rest
     out[cell] = acc;
 }
 
-// the same sums, four disparities per thread (D % 4 == 0, 16-byte aligned volumes): a quarter of the load instructions
-template <bool HORIZ>
-__global__ void __launch_bounds__(256) agg_pass_exact4_kernel(const float4* __restrict__ in, float4* __restrict__ out,
-                                                              const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
-                                                              int H, int W, int D4) {
-    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t ncell = (size_t)H * W * D4;
-    if (cell >= ncell) return;
-    const size_t pix = cell / D4;
-    const int d4 = (int)(cell - pix * D4);
-    const uchar4 a = arms[pix];
-    const int pos = HORIZ ? (int)(pix % W) : (int)(pix / W), len = HORIZ ? W : H;
-    const int lo = -min(HORIZ ? (int)a.x : (int)a.z, pos);
-    const int hi = min(HORIZ ? (int)a.y : (int)a.w, len - 1 - pos);
-    const long long step = HORIZ ? (long long)D4 : (long long)W * D4;
-    const float4* p = in + (long long)pix * D4 + d4 + lo * step;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = lo; t <= hi; ++t) {
-        const float4 v = *p;
-        acc.x = __fadd_rn(acc.x, v.x);
-        acc.y = __fadd_rn(acc.y, v.y);
-        acc.z = __fadd_rn(acc.z, v.z);
-        acc.w = __fadd_rn(acc.w, v.w);
-        p += step;
-    }
-    if (sup) {
-        const float c = (float)(int)sup[pix];
-        acc.x = __fdiv_rn(acc.x, c);
-        acc.y = __fdiv_rn(acc.y, c);
-        acc.z = __fdiv_rn(acc.z, c);
-        acc.w = __fdiv_rn(acc.w, c);
-    }
-    out[cell] = acc;
-}
-
 // Four disparities AND four consecutive positions of the line per thread: the windows of neighbouring positions overlap
 // almost completely, so each tap row is loaded once for the four outputs and added (in ascending tap order, exactly the
 // reference's order for every output) to the ones whose window contains it.  A quarter of the L1 traffic again.
@@ -223,7 +189,7 @@ constexpr int EXACT_NP = SMT_EXACT_NP;  // consecutive positions per thread
 template <bool HORIZ>
 __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __restrict__ in, float4* __restrict__ out,
                                                                const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup,
-                                                               int H, int W, int D4) {
+                                                               int H, int W, int D4, int st_lo, int st_hi) {
     const int len = HORIZ ? W : H, nlines = HORIZ ? H : W;
     const int ngrp = (len + EXACT_NP - 1) / EXACT_NP;
     const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,8 +206,8 @@ __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __r
     for (int i = 0; i < EXACT_NP; ++i) {
         const int pos = p0 + i;
         s[i] = 1;
-        e[i] = 0;  // empty window for positions beyond the line
-        if (pos < len) {
+        e[i] = 0;  // empty window for positions beyond the line or outside the stored range
+        if (pos < len && pos >= st_lo && pos < st_hi) {
             const uchar4 a = arms[pbase + pstride * pos];
             s[i] = max(pos - (HORIZ ? (int)a.x : (int)a.z), 0);  // clamps: see agg_pass_exact_kernel
             e[i] = min(pos + (HORIZ ? (int)a.y : (int)a.w), len - 1);
@@ -269,7 +235,7 @@ __global__ void __launch_bounds__(256) agg_pass_exact44_kernel(const float4* __r
 #pragma unroll
     for (int i = 0; i < EXACT_NP; ++i) {
         const int pos = p0 + i;
-        if (pos < len) {
+        if (pos < len && pos >= st_lo && pos < st_hi) {
             const long long pix = pbase + pstride * pos;
             float4 r = acc[i];
             if (sup) {
@@ -291,27 +257,30 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
 
 // one reference-order pass (taps added sequentially in ascending order, starting from 0.0f)
 smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const uint8_t* arms8, const uint16_t* s, int H, int W, int D,
-                              int horiz) {
+                              int horiz, int st_lo, int st_hi) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
+    if (st_hi <= 0) {
+        st_lo = 0;
+        st_hi = horiz ? W : H;
+    }
     const size_t ncell = (size_t)H * W * D;
     const unsigned grid = cdiv((long long)ncell, 256);
     const bool vec4 = D % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-    const unsigned grid4 = cdiv((long long)(ncell / 4), 256);
     if (vec4) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
         float4* d4 = reinterpret_cast<float4*>(dst);
         {
             const long long items = (long long)(horiz ? H : W) * (((horiz ? W : H) + EXACT_NP - 1) / EXACT_NP) * (D / 4);
             if (horiz)
-                SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
+                SMT_LAUNCH(ctx, agg_pass_exact44_kernel<true>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4, st_lo, st_hi);
             else
-                SMT_LAUNCH(ctx, agg_pass_exact44_kernel<false>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4);
+                SMT_LAUNCH(ctx, agg_pass_exact44_kernel<false>, cdiv(items, 256), 256, 0, s4, d4, arms, s, H, W, D / 4, st_lo, st_hi);
         }
     } else {
         if (horiz)
-            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, src, dst, arms, s, H, W, D);
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<true>, grid, 256, 0, src, dst, arms, s, H, W, D, st_lo, st_hi);
         else
-            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, src, dst, arms, s, H, W, D);
+            SMT_LAUNCH(ctx, agg_pass_exact_kernel<false>, grid, 256, 0, src, dst, arms, s, H, W, D, st_lo, st_hi);
     }
     return SMT_OK;
 }

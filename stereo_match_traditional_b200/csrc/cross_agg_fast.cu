@@ -13,16 +13,6 @@
 // the float-pair kernels.
 #include "common.cuh"
 
-smt_status_t k_transpose_maps(smt_ctx* ctx, const uint8_t* arms8, const uint16_t* sup, int H, int W, uint8_t* armsT, uint16_t* supT);
-smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                            int horiz, bool nonneg, float bias, int tmaps, const int* redo);  // cross_agg_seq.cu
-smt_status_t k_fx_state_reset(smt_ctx* ctx, int* state, bool new_aggregation, size_t ntasks);
-bool fx_quantum(float vmax, float* inv_q, float* q);  // cross_agg_fx.cu
-smt_status_t k_agg_fx_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                           int horiz, int tmaps, float inv_q, float q, int* state);
-smt_status_t k_agg_fx_pair(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                           int horiz, int tmaps, float inv_q, float q, int* state);
-
 namespace {
 
 struct Pass {

@@ -147,7 +147,7 @@ __device__ __forceinline__ void fx1_chunk(FxAcc& acc, unsigned& bad, FxPre& pre,
                                           int tbm, int len, bool act, const float* __restrict__ src_next, float* __restrict__ dst_first,
                                           long long step_rt, long long mbase, long long mstride, int horiz,
                                           const unsigned* __restrict__ arms, const uint16_t* __restrict__ sup, unsigned char* ring_col,
-                                          FxDesc* desc, int lane, float inv_q, float q, unsigned vm1, int zero) {
+                                          FxDesc* desc, int lane, float inv_q, float q, unsigned vm1, int zero, int st_lo, int st_hi) {
     const long long step = CSTEP ? (long long)CSTEP : step_rt;
     const long long step_b = step * 4;
     // ---- (1a) descriptors of this chunk's outputs (position tb - 35 + lane) from the arm word / count fetched a chunk ago
@@ -212,7 +212,7 @@ __device__ __forceinline__ void fx1_chunk(FxAcc& acc, unsigned& bad, FxPre& pre,
             }
             if (k >= FX_RLAG) {
                 const int kk = k - FX_RLAG;
-                const bool inside = !EDGE || (tb - FX_LOOK + kk >= 0 && tb - FX_LOOK + kk < len);  // warp-uniform
+                const bool inside = !EDGE || (tb - FX_LOOK + kk >= st_lo && tb - FX_LOOK + kk < st_hi);  // warp-uniform
                 float r = __uint2float_rn(eb[kk] - ea[kk]);
                 if (PRIMED) {
                     r = fx_div(r, dsc[kk].bq, dsc[kk].yq);
@@ -237,7 +237,7 @@ template <bool PRIMED, int CSTEP>
 __global__ void __launch_bounds__(FX1_WARPS * 32, PRIMED ? 3 : 4)
     agg_fx1_kernel(const float* __restrict__ in, float* __restrict__ out, const unsigned* __restrict__ arms,
                    const uint16_t* __restrict__ sup, int H, int W, int D, int horiz, int tmaps, float inv_q, float q, unsigned vm1,
-                   int* __restrict__ state, int zero) {
+                   int* __restrict__ state, int zero, int st_lo, int st_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ FxDesc s_desc_all[FX1_WARPS][FX_CH];
     if (*reinterpret_cast<volatile int*>(state + FX_ST_ESCALATED) != 0) return;  // the float-pair passes do the whole sweep
@@ -273,12 +273,15 @@ __global__ void __launch_bounds__(FX1_WARPS * 32, PRIMED ? 3 : 4)
         const int tb = o * FX_CH;                                                                                             \
         const float* src_next = src + step * (tb + FX_CH);                                                                    \
         float* dst_first = dst + step * (tb - FX_LOOK);                                                                       \
-        if (full && tb - FX_LOOK >= 0 && tb + 2 * FX_CH <= len)                                                               \
+        /* interior: every load and every output of the chunk is inside the line and inside the stored range */            \
+        if (full && tb - FX_LOOK >= st_lo && tb - FX_LOOK + FX_CH <= st_hi && tb + 2 * FX_CH <= len)                          \
             fx1_chunk<PRIMED, false, CSTEP>(acc, bad, pre, USE, LOAD, tb, tbm, len, act, src_next, dst_first, step, mbase,    \
-                                            mstride, horiz, arms, sup, ring_col, s_desc, lane, inv_q, q, vm1, zero);          \
+                                            mstride, horiz, arms, sup, ring_col, s_desc, lane, inv_q, q, vm1, zero, st_lo,    \
+                                            st_hi);                                                                           \
         else                                                                                                                  \
             fx1_chunk<PRIMED, true, CSTEP>(acc, bad, pre, USE, LOAD, tb, tbm, len, act, src_next, dst_first, step, mbase,     \
-                                           mstride, horiz, arms, sup, ring_col, s_desc, lane, inv_q, q, vm1, zero);           \
+                                           mstride, horiz, arms, sup, ring_col, s_desc, lane, inv_q, q, vm1, zero, st_lo,     \
+                                           st_hi);                                                                            \
         tbm = tbm == FX_R - FX_CH ? 0 : tbm + FX_CH;                                                                          \
         ++o;                                                                                                                  \
     }
@@ -534,13 +537,13 @@ constexpr unsigned FX_VMIN = 1u << 19;  // smallest non-zero tap the fixed-point
 
 template <bool PRIMED, int CSTEP>
 static smt_status_t launch_fx1(smt_ctx* ctx, const float* in, float* out, const unsigned* arms, const uint16_t* sup, int H, int W, int D,
-                               int horiz, int tmaps, float inv_q, float q, int* state) {
+                               int horiz, int tmaps, float inv_q, float q, int* state, int st_lo, int st_hi) {
     constexpr size_t smem = (size_t)FX1_WARPS * Fx1Cfg<PRIMED>::SMEM_PER_WARP;
     static bool done[64] = {};
     SMT_TRY(fx_set_smem(ctx, agg_fx1_kernel<PRIMED, CSTEP>, done[ctx->device & 63], smem));
     const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
     SMT_LAUNCH(ctx, (agg_fx1_kernel<PRIMED, CSTEP>), cdiv(nwarps, FX1_WARPS), FX1_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz, tmaps,
-               inv_q, q, FX_VMIN - 1u, state, 0);
+               inv_q, q, FX_VMIN - 1u, state, 0, st_lo, st_hi);
     return SMT_OK;
 }
 
@@ -576,14 +579,20 @@ bool fx_quantum(float vmax, float* inv_q, float* q) {
 }
 
 // one pass; sup != nullptr makes it the dividing pass.  `state`: the sweep's redo state (FX_ST_*), count reset by the caller.
+// st_lo, st_hi: only outputs at positions [st_lo, st_hi) of each line are stored (row bands: a vertical pass must leave the
+// halo rows of its output alone, the neighbours write those); st_hi <= 0 means the whole line.
 smt_status_t k_agg_fx_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                           int horiz, int tmaps, float inv_q, float q, int* state) {
+                           int horiz, int tmaps, float inv_q, float q, int* state, int st_lo, int st_hi) {
     const unsigned* arms = reinterpret_cast<const unsigned*>(arms8);
     const long long step = horiz ? D : (long long)W * D;
+    if (st_hi <= 0) {
+        st_lo = 0;
+        st_hi = horiz ? W : H;
+    }
 #define SMT_FX1_DISPATCH(PRIMED_)                                                                                                   \
-    if (step == FX_STEP_H256) return launch_fx1<PRIMED_, FX_STEP_H256>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state);   \
-    if (step == FX_STEP_V1080P) return launch_fx1<PRIMED_, FX_STEP_V1080P>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state); \
-    return launch_fx1<PRIMED_, 0>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state);
+    if (step == FX_STEP_H256) return launch_fx1<PRIMED_, FX_STEP_H256>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state, st_lo, st_hi);   \
+    if (step == FX_STEP_V1080P) return launch_fx1<PRIMED_, FX_STEP_V1080P>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state, st_lo, st_hi); \
+    return launch_fx1<PRIMED_, 0>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state, st_lo, st_hi);
     if (sup) {
         SMT_FX1_DISPATCH(true)
     }

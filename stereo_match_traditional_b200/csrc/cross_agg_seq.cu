@@ -138,7 +138,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
                                           const float* src_next, float* dst_first, long long step_rt,
                                           long long pbase, long long pstride, int horiz, const uchar4* __restrict__ arms,
                                           const uint16_t* __restrict__ sup, unsigned char* ring_col, Desc* desc, int lane,
-                                          float2* __restrict__ wta_first, long long wta_step, int d, int zero) {
+                                          float2* __restrict__ wta_first, long long wta_step, int d, int zero, int st_lo, int st_hi) {
     const long long step = CSTEP ? (long long)CSTEP : step_rt;
     const long long step_b = step * 4;  // byte steps on char pointers: one 64-bit add per address instead of index + shift
     // ORDER MATTERS.  ptxas puts every global load of this kernel on ONE scoreboard (SB5 in the SASS), and a scoreboard is a
@@ -232,7 +232,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
             }
             if (k >= SEQ_RLAG) {
                 const int kk = k - SEQ_RLAG;
-                const bool inside = !EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len);  // warp-uniform
+                const bool inside = !EDGE || (tb - SEQ_LOOK + kk >= st_lo && tb - SEQ_LOOK + kk < st_hi);  // warp-uniform
                 float r = __fadd_rn(__fsub_rn(eb[kk].x, ea[kk].x), __fsub_rn(eb[kk].y, ea[kk].y));
                 if (HAS_SUP) r = div_by_count(r, dsc[kk].cnt, dsc[kk].rcp);
                 if (WTA) {
@@ -265,7 +265,7 @@ __device__ __forceinline__ void seq_chunk(pair2& acc, Prefetched& pre, float (&v
             for (int u = 0; u < SEQ_G; ++u) {
                 const int kk = k - (SEQ_G - 1) + u;
                 const Desc ds = desc[kk];  // broadcast
-                if (!EDGE || (tb - SEQ_LOOK + kk >= 0 && tb - SEQ_LOOK + kk < len)) {
+                if (!EDGE || (tb - SEQ_LOOK + kk >= st_lo && tb - SEQ_LOOK + kk < st_hi)) {
                     const float2 ea = *reinterpret_cast<const float2*>(ring_col + ds.offa);
                     const float2 eb = *reinterpret_cast<const float2*>(ring_col + ds.offb);
                     float r = __fadd_rn(__fsub_rn(eb.x, ea.x), __fsub_rn(eb.y, ea.y));
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
                                                     
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
                                                      int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero, int tmaps,
-                                                     const int* __restrict__ redo) {
+                                                     const int* __restrict__ redo, int st_lo, int st_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
@@ -358,14 +358,14 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
         float2* wta_first = WTA ? wta_partial + (pbase + pstride * (tb - SEQ_LOOK)) * nchunk + chunk : nullptr;               \
         const long long wta_step = pstride * nchunk;                                                                          \
         /* interior: the chunk being loaded is inside the line, all outputs of this chunk are, all lanes active */           \
-        if (full && tb - SEQ_LOOK >= 0 && tb + (SEQ_AHEAD + 1) * SEQ_CH <= len)                                               \
+        if (full && tb - SEQ_LOOK >= st_lo && tb - SEQ_LOOK + SEQ_CH <= st_hi && tb + (SEQ_AHEAD + 1) * SEQ_CH <= len)        \
             seq_chunk<NONNEG, HAS_SUP, false, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, mbase,       \
                                                    mstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,               \
-                                                   wta_step, chunk * 32, zero);                                               \
+                                                   wta_step, chunk * 32, zero, st_lo, st_hi);                                 \
         else                                                                                                                  \
             seq_chunk<NONNEG, HAS_SUP, true, WTA, CSTEP>(acc, pre, USE, LOAD, tb, len, act, src_next, dst_first, step, mbase,        \
                                                   mstride, horiz, arms, sup, ring_col, s_desc, lane, wta_first,                \
-                                                  wta_step, chunk * 32, zero);                                                \
+                                                  wta_step, chunk * 32, zero, st_lo, st_hi);                                  \
         ++o;                                                                                                                  \
     }
     for (int o = 0; o < nouter;) {
@@ -383,7 +383,12 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
 
 template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
-                               int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0, const int* redo = nullptr) {
+                               int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0, const int* redo = nullptr, int st_lo = 0,
+                               int st_hi = 0) {
+    if (st_hi <= 0) {
+        st_lo = 0;
+        st_hi = horiz ? W : H;
+    }
     constexpr size_t smem = (size_t)SEQ_WARPS * SEQ_SMEM_PER_WARP;
     static bool attr_set_dev[64] = {};  // function attributes are per device
     bool& attr_set = attr_set_dev[ctx->device & 63];
@@ -407,32 +412,24 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
             attr2 = true;
         }
         SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
-                   horiz, bias, wta_partial, 0, tmaps, redo);
+                   horiz, bias, wta_partial, 0, tmaps, redo, st_lo, st_hi);
         return SMT_OK;
     }
     SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
-               bias, wta_partial, 0, tmaps, redo);
+               bias, wta_partial, 0, tmaps, redo, st_lo, st_hi);
     return SMT_OK;
 }
 
 }  // namespace
 
-smt_status_t k_agg_exact_pass(smt_ctx* ctx, const float* src, float* dst, const uint8_t* arms8, const uint16_t* s, int H, int W, int D,
-                              int horiz);  // cross_agg.cu
-smt_status_t k_arms_max(smt_ctx* ctx, const uint8_t* arms8, size_t npix, int* longest);  // cross_agg.cu (synchronises)
-bool fx_quantum(float vmax, float* inv_q, float* q);  // cross_agg_fx.cu
-smt_status_t k_agg_fx_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                           int horiz, int tmaps, float inv_q, float q, int* state);
-smt_status_t k_fx_state_reset(smt_ctx* ctx, int* state, bool new_aggregation, size_t ntasks);
-
 smt_status_t k_agg_seq_pass(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, const uint16_t* sup, int H, int W, int D,
-                            int horiz, bool nonneg, float bias, int tmaps, const int* redo) {
+                            int horiz, bool nonneg, float bias, int tmaps, const int* redo, int st_lo, int st_hi) {
     const uchar4* arms = reinterpret_cast<const uchar4*>(arms8);
     if (nonneg)
-        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo)
-                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo);
-    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo)
-               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo);
+        return sup ? launch_seq<true, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo, st_lo, st_hi)
+                   : launch_seq<true, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo, st_lo, st_hi);
+    return sup ? launch_seq<false, true, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo, st_lo, st_hi)
+               : launch_seq<false, false, false>(ctx, in, out, arms, sup, H, W, D, horiz, bias, nullptr, tmaps, redo, st_lo, st_hi);
 }
 
 // [H][W] -> [W][H] copies of the arm words and of one support-count map for the vertical walks
@@ -478,6 +475,32 @@ smt_status_t k_fx_state_reset(smt_ctx* ctx, int* state, bool new_aggregation, si
     return SMT_OK;
 }
 
+smt_status_t k_cross_sweep(smt_ctx* ctx, int iters, int sweep, const float* vol_in, float* vol_out, const uint8_t* arms,
+                           const uint16_t* sup_hfirst, const uint16_t* sup_vfirst, int rows, int cols, int D, float vmax,
+                           smt_sum_mode_t mode, bool first_of_aggregation, int st_lo, int st_hi, size_t ntasks_whole) {
+    (void)iters;
+    StageTimer t(ctx, ST_AGGREGATE);
+    // direction and divisor of sweep s (cross_aggregator.cpp:102-117): horizontal first on even iterations, second pass divides
+    const bool hfirst = (sweep / 2) % 2 == 0, second = sweep % 2 == 1;
+    const int horiz = (hfirst != second) ? 1 : 0;
+    const uint16_t* sup = second ? (hfirst ? sup_hfirst : sup_vfirst) : nullptr;
+    if (mode == SMT_SUM_REFERENCE_ORDER) return k_agg_exact_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, st_lo, st_hi);
+    const bool nonneg = vmax > 0.f && vmax < 1e30f;
+    float b = 1.f;
+    while (nonneg && b < vmax) b *= 2.f;
+    float inv_q = 0.f, q = 0.f;
+    const bool fx = nonneg && fx_quantum(vmax, &inv_q, &q);
+    size_t ntasks = (size_t)(rows > cols ? rows : cols) * ((D + 31) / 32);
+    if (ntasks_whole > ntasks) ntasks = ntasks_whole;
+    int* state = fx ? smt_redo_state(ctx, ntasks) : nullptr;
+    if (fx && !state) return smt_fail(ctx, SMT_ERR_OOM, "cross sweep: redo list allocation failed");
+    if (fx) {
+        SMT_TRY(k_fx_state_reset(ctx, state, first_of_aggregation, ntasks));
+        SMT_TRY(k_agg_fx_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, 0, inv_q, q, state, st_lo, st_hi));
+    }
+    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, second ? b * 128.f : b, 0, state, st_lo, st_hi);
+}
+
 // ---------------------------------------------------------------------------------------------- per-sweep C ABI (row bands)
 extern "C" {
 
@@ -500,35 +523,18 @@ smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int32_t swee
     SMT_REQUIRE(ctx, space == SMT_DEVICE, SMT_ERR_UNSUPPORTED, "smt_aggregate_cross_sweep: device memspace only");
     SMT_REQUIRE(ctx, vol_in && vol_out && vol_in != vol_out && arms && sup_hfirst && sup_vfirst && rows > 0 && cols > 0 && D > 0,
                 SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: bad argument");
-    int32_t horiz = 0, divides = 0;
-    if (smt_cross_sweep_info(iters, sweep, &horiz, &divides) != SMT_OK)
-        return smt_fail(ctx, SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: sweep %d outside 0..%d", sweep, 2 * iters - 1);
+    SMT_REQUIRE(ctx, sweep >= 0 && sweep < 2 * iters, SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: sweep outside 0..2*iters-1");
+    SMT_REQUIRE(ctx, mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST, SMT_ERR_INVALID_ARG,
+                "smt_aggregate_cross_sweep: unknown sum mode");
     DeviceGuard dev_guard(ctx->device);
-    StageTimer t(ctx, ST_AGGREGATE);
-    const bool hfirst = (sweep / 2) % 2 == 0;
-    const uint16_t* sup = divides ? (hfirst ? sup_hfirst : sup_vfirst) : nullptr;
-    if (mode == SMT_SUM_REFERENCE_ORDER) return k_agg_exact_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz);
-    SMT_REQUIRE(ctx, mode == SMT_SUM_FAST, SMT_ERR_INVALID_ARG, "smt_aggregate_cross_sweep: unknown sum mode");
-    const bool nonneg = vmax > 0.f && vmax < 1e30f;
-    float b = 1.f;
-    while (nonneg && b < vmax) b *= 2.f;
-    float inv_q = 0.f, q = 0.f;
-    const bool fx = nonneg && fx_quantum(vmax, &inv_q, &q);
-    const size_t ntasks = (size_t)(rows > cols ? rows : cols) * ((D + 31) / 32);
-    int* state = fx ? smt_redo_state(ctx, ntasks) : nullptr;
-    if (fx && !state) return smt_fail(ctx, SMT_ERR_OOM, "smt_aggregate_cross_sweep: redo list allocation failed");
-    if (sweep == 0) {
+    if (sweep == 0 && mode == SMT_SUM_FAST) {
         // the streaming kernels keep 72 prefix entries per line: arms beyond 34 would wrap onto stale entries
         int longest = 0;
         SMT_TRY(k_arms_max(ctx, arms, (size_t)rows * cols, &longest));
         if (longest > 34)
             return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "smt_aggregate_cross_sweep: SMT_SUM_FAST supports arms <= 34, the maps hold %d", longest);
     }
-    if (fx) {
-        SMT_TRY(k_fx_state_reset(ctx, state, sweep == 0, ntasks));
-        SMT_TRY(k_agg_fx_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, 0, inv_q, q, state));
-    }
-    return k_agg_seq_pass(ctx, vol_in, vol_out, arms, sup, rows, cols, D, horiz, nonneg, divides ? b * 128.f : b, 0, state);
+    return k_cross_sweep(ctx, iters, sweep, vol_in, vol_out, arms, sup_hfirst, sup_vfirst, rows, cols, D, vmax, mode, sweep == 0);
 }
 
 smt_status_t smt_aggregate_fast_status(smt_ctx* ctx, int32_t* used_float_pairs) {

@@ -6,6 +6,11 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+# The in-process band tests run several bands on ONE device, each on its own streams, and a band's stream may spin on a
+# flag another band's stream has to set: the streams must not share a hardware queue (8 by default).  One process per GPU,
+# the deployment this emulates, has no such coupling.  Must be set before the process creates its CUDA context.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))

@@ -19,6 +19,10 @@ def test_band_partition():
     assert bands[3].nrows == 540 + 2 * HALO
     with pytest.raises(ValueError):
         make_band(1, 8, 100)          # 13-row bands cannot hold a 34-row halo
+    # rows=290, world=8: ranks 0-6 would own 37 rows and only rank 7 31 -- every rank must refuse, or 0-6 would wait for 7
+    for r in range(8):
+        with pytest.raises(ValueError):
+            make_band(r, 8, 290)
 
 
 def _free_port():
