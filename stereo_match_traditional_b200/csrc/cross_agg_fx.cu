@@ -565,6 +565,12 @@ constexpr int FX_STEP_H256 = 256, FX_STEP_V1080P = 1920 * 256;
 
 }  // namespace
 
+#ifdef SMT_DEV_VARIANTS
+#include <cstdlib>
+smt_status_t k_agg_fx_pass_tma(smt_ctx* ctx, const float* in, float* out, const uint8_t* arms8, int H, int W, int D, int horiz, int tmaps,
+                               float inv_q, float q, int* state);
+#endif
+
 // quantum of the fixed-point prefixes for costs below `vmax`: q = S * 2^-25 with S the power of two >= vmax, so that 69
 // taps stay below 2^32 quanta and dyadic inputs (integer-valued volumes) are represented exactly.  Returns false when the
 // fixed-point form does not apply (unknown sign / range, or a range whose quantum is not a normal float).
@@ -596,6 +602,12 @@ smt_status_t k_agg_fx_pass(smt_ctx* ctx, const float* in, float* out, const uint
     if (sup) {
         SMT_FX1_DISPATCH(true)
     }
+#ifdef SMT_DEV_VARIANTS
+    // A/B: the bulk-copy staged form of the non-dividing pass (dev/fx1_tma.cuh), full lines only
+    static const bool use_tma = getenv("SMT_FX1_TMA") != nullptr;
+    if (use_tma && D % 32 == 0 && st_lo == 0 && st_hi == (horiz ? W : H))
+        return k_agg_fx_pass_tma(ctx, in, out, arms8, H, W, D, horiz, tmaps, inv_q, q, state);
+#endif
     SMT_FX1_DISPATCH(false)
 #undef SMT_FX1_DISPATCH
 }
@@ -609,3 +621,7 @@ smt_status_t k_agg_fx_pair(smt_ctx* ctx, const float* in, float* out, const uint
     if (step == FX_STEP_V1080P) return launch_fx2<FX_STEP_V1080P>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state);
     return launch_fx2<0>(ctx, in, out, arms, sup, H, W, D, horiz, tmaps, inv_q, q, state);
 }
+
+#ifdef SMT_DEV_VARIANTS
+#include "dev/fx1_tma.cuh"
+#endif
