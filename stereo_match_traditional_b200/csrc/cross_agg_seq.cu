@@ -317,13 +317,29 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
     long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
     // redo != nullptr: this launch is queued behind a fixed-point sweep (cross_agg_fx.cu) and only redoes the (line, chunk)
     // tasks that sweep put on its list -- or every task once the sweep escalated
+    // A listed line is cut into gridDim.y segments walked by different warps: a handful of warps each walking a whole line
+    // would leave the launch bound by the latency of one walk (~50 us at 1920 positions).  A segment starts its prefix
+    // 48 positions early (outputs only read prefix entries up to 34 positions back) and stores its own positions only.
+    // Not for in-place launches (in == out): a segment's lead-in would read what its neighbour has already overwritten.
+    int seg_lo = 0, seg_hi = 0x7fffffff;
     if (redo && *reinterpret_cast<const volatile int*>(redo + FX_ST_ESCALATED) == 0) {
         if (wg >= *reinterpret_cast<const volatile int*>(redo + FX_ST_COUNT)) return;
         wg = redo[FX_ST_LIST + wg];
+        if (gridDim.y > 1) {
+            const int seg_len = ((horiz ? W : H) + (int)gridDim.y - 1) / (int)gridDim.y;
+            seg_lo = (int)blockIdx.y * seg_len;
+            seg_hi = seg_lo + seg_len;
+        }
+    } else if (blockIdx.y > 0) {
+        return;  // whole sweeps are walked line by line
     }
     const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
     const int len = horiz ? W : H;
-    if (line >= (horiz ? H : W)) return;  // whole warp; warps never synchronise with each other
+    if (line >= (horiz ? H : W) || seg_lo >= len) return;  // whole warp; warps never synchronise with each other
+    st_lo = max(st_lo, seg_lo);
+    st_hi = min(st_hi, seg_hi);
+    const int o_first = max(0, (seg_lo - 48) / SEQ_CH);                                      // first chunk walked
+    const int o_last = seg_hi >= len ? 0x7fffffff : (seg_hi + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;  // one past the last
     const int d = chunk * 32 + lane;
     const bool act = d < D;
     const bool full = chunk * 32 + 32 <= D;  // every lane active: the interior path needs no lane predicate
@@ -343,13 +359,14 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
     float va[SEQ_CH], vb[SEQ_CH], vc[SEQ_AHEAD == 2 ? SEQ_CH : 1];
 #pragma unroll
     for (int k = 0; k < SEQ_CH; ++k) {
-        va[k] = (k < len && act) ? __ldcs(src + step * k) : 0.f;
-        if (SEQ_AHEAD == 2) vb[k] = (SEQ_CH + k < len && act) ? __ldcs(src + step * (SEQ_CH + k)) : 0.f;
+        const int p = o_first * SEQ_CH + k;
+        va[k] = (p < len && act) ? __ldcs(src + step * p) : 0.f;
+        if (SEQ_AHEAD == 2) vb[k] = (SEQ_CH + p < len && act) ? __ldcs(src + step * (SEQ_CH + p)) : 0.f;
     }
 
     Prefetched pre{0u, 1};  // chunk 0 outputs positions -35..-4: nothing to fetch; its call fetches chunk 1's
     // chunk o covers prefix positions [32*o, 32*o+32) and outputs [32*o-35, 32*o-3); outputs end at len-1
-    const int nouter = (len + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;
+    const int nouter = min((len + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH, o_last);
 #define SMT_SEQ_STEP(USE, LOAD)                                                                                               \
     if (o < nouter) {                                                                                                         \
         const int tb = o * SEQ_CH;                                                                                            \
@@ -368,7 +385,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
                                                   wta_step, chunk * 32, zero, st_lo, st_hi);                                  \
         ++o;                                                                                                                  \
     }
-    for (int o = 0; o < nouter;) {
+    for (int o = o_first; o < nouter;) {
 #if SMT_SEQ_AHEAD == 2
         SMT_SEQ_STEP(va, vc)
         SMT_SEQ_STEP(vb, va)
@@ -385,6 +402,8 @@ template <bool NONNEG, bool HAS_SUP, bool WTA>
 static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const uchar4* arms, const uint16_t* sup, int H, int W, int D,
                                int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0, const int* redo = nullptr, int st_lo = 0,
                                int st_hi = 0) {
+    // redo launches that do not run in place cut the listed lines into segments (see the kernel)
+    const unsigned nseg = (redo && in != out) ? (unsigned)max(1, min(8, (horiz ? W : H) / 192)) : 1u;
     if (st_hi <= 0) {
         st_lo = 0;
         st_hi = horiz ? W : H;
@@ -411,11 +430,11 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
                                                (int)cudaSharedmemCarveoutMaxShared));
             attr2 = true;
         }
-        SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
+        SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), dim3(cdiv(nwarps, SEQ_WARPS), nseg), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
                    horiz, bias, wta_partial, 0, tmaps, redo, st_lo, st_hi);
         return SMT_OK;
     }
-    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), cdiv(nwarps, SEQ_WARPS), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
+    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), dim3(cdiv(nwarps, SEQ_WARPS), nseg), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
                bias, wta_partial, 0, tmaps, redo, st_lo, st_hi);
     return SMT_OK;
 }

@@ -25,6 +25,13 @@ __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
+// three-input minimum (FMNMX3 on sm_100a)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 template <int N, int VW>
 __device__ __forceinline__ void load_row(const float* __restrict__ p, float (&r)[N], int nvalid) {
     if (VW == 4) {
@@ -100,6 +107,7 @@ __global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__
         }
     }
 
+    const bool p1_nonneg = p1 >= 0.f;
     float prev[DPL];
 #pragma unroll
     for (int k = 0; k < DPL; ++k) prev[k] = PAD;
@@ -182,9 +190,15 @@ __global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__
                             const float l1 = prev[k];
                             const float lm = (k == 0) ? up_nb : prev[k - 1];
                             const float lp = (k == DPL - 1) ? dn_nb : prev[k + 1];
-                            const float l2 = VERT ? __fadd_rn(l1, p1) : __fadd_rn(lm, p1);  // (:238) vs (:177)
-                            const float l3 = __fadd_rn(lp, p1);
-                            const float mn = fminf(fminf(l1, l2), fminf(l3, l4));
+                            // min(l1, l2, l3, l4) with l3 = lp + p1, l4 = m + p2 and l2 = lm + p1 (:177), resp. l2 = l1 + p1 for
+                            // the up/down paths (:238).  Rounding is monotonic, so min(lm + p1, lp + p1) == min(lm, lp) + p1
+                            // bit for bit, and l1 + p1 >= l1 for p1 >= 0 never wins: one add and a three-input minimum.
+                            float mn;
+                            if (VERT)
+                                mn = p1_nonneg ? fmin3(l1, __fadd_rn(lp, p1), l4)
+                                               : fmin3(fminf(l1, __fadd_rn(l1, p1)), __fadd_rn(lp, p1), l4);
+                            else
+                                mn = fmin3(l1, __fadd_rn(fminf(lm, lp), p1), l4);
                             const float vv = __fsub_rn(__fadd_rn(cC[v][k], mn), m);
                             cur[k] = (k < nvalid) ? vv : PAD;
                         }
@@ -193,7 +207,8 @@ __global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__
                     // minimum over d of the new row (capped by the 0xffff pads, :162-166,:169,:182)
                     float lm_ = PAD;
 #pragma unroll
-                    for (int k = 0; k < DPL; ++k) lm_ = fminf(lm_, cur[k]);
+                    for (int k = 0; k + 1 < DPL; k += 2) lm_ = fmin3(lm_, cur[k], cur[k + 1]);
+                    if (DPL & 1) lm_ = fminf(lm_, cur[DPL - 1]);
                     m = key2f(__reduce_min_sync(0xffffffffu, f2key(lm_)));
 #pragma unroll
                     for (int k = 0; k < DPL; ++k) prev[k] = cur[k];
