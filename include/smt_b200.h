@@ -138,6 +138,30 @@ SMT_API smt_status_t smt_aggregate_cross_sweep(smt_ctx* ctx, int32_t iters, int3
                                                const uint16_t* sup_vfirst, int32_t rows, int32_t cols, int32_t D,
                                                float vmax, smt_sum_mode_t mode, smt_memspace_t space);
 
+/* ------------------------------------------------------------------------------------------------ multi-step refinement
+ * Iterative region voting, proper interpolation and depth-discontinuity adjustment (Mei et al. 2011, section 2.4), which
+ * BASELINE.json's north_star names.  PARITY UNPINNED: the reference implements none of them -- only the option fields
+ * irv_ts, irv_th, do_discontinuity_adjustment exist (CBLSM/adcensus_types.h:58-59,65) and nothing reads them -- so the
+ * specification is fixed in oracle/port/oracle_port.c (orc_refine_*) and these entry points are bit-identical to that.
+ * disp: float32 [rows][cols], +inf = invalid (what LeftRightConsistency writes, PostProcessing.h:93,131), updated in place.
+ * cls: uint8 [rows][cols], 0 valid / 1 occlusion / 2 mismatch, updated in place (filled pixels become 0);
+ *   smt_invalid_class_map builds it from LeftRightConsistency's two (row, col) lists.
+ * smt_refine_region_voting: `iters` synchronous iterations; an invalid pixel takes the first most frequent valid disparity of
+ *   its cross support region (arms: CrossAggregator's {left,right,top,bottom} bytes, cross_aggregator.h:17-20) if the region
+ *   holds more than ts valid pixels and that disparity's share exceeds th (defaults of the unused fields: ts 20, th 0.4).
+ * smt_refine_interpolate: an invalid pixel looks along 16 directions for the first valid disparity (at most max_len-1 steps);
+ *   an occlusion takes the smallest one, a mismatch the one whose BGR colour is closest to its own.
+ * smt_refine_discontinuity: on edges of the disparity map (3x3 Sobel, |gx|+|gy| > thres) a pixel takes its left or right
+ *   neighbour's disparity when the aggregated cost volume cost [rows][cols][D] rates it lower at this pixel. */
+SMT_API smt_status_t smt_invalid_class_map(smt_ctx* ctx, const int32_t* occ, int32_t n_occ, const int32_t* mis, int32_t n_mis,
+                                           int32_t rows, int32_t cols, uint8_t* cls, smt_memspace_t space);
+SMT_API smt_status_t smt_refine_region_voting(smt_ctx* ctx, float* disp, uint8_t* cls, const uint8_t* arms, int32_t rows,
+                                              int32_t cols, int32_t D, int32_t ts, float th, int32_t iters, smt_memspace_t space);
+SMT_API smt_status_t smt_refine_interpolate(smt_ctx* ctx, float* disp, uint8_t* cls, const uint8_t* bgr, int32_t rows, int32_t cols,
+                                            int32_t max_len, smt_memspace_t space);
+SMT_API smt_status_t smt_refine_discontinuity(smt_ctx* ctx, float* disp, const float* cost, int32_t rows, int32_t cols, int32_t D,
+                                              float thres, smt_memspace_t space);
+
 /* ------------------------------------------------------------------------------------------------ row-band split
  * One very large frame split into row bands over several GPUs, for the cost and cross-aggregation stages
  * (BASELINE.json configs[4]; the reference has no counterpart: CrossAggregator::Aggregate, CBLSM/cross_aggregator.cpp:89-118,

@@ -211,6 +211,46 @@ class Oracle:
         self._fn("fill_the_hole_fixed" if fixed else "fill_the_hole")(row, col, int(disp_range), _p(d, _f32p), _p(o, _i32p), len(o), _p(m, _i32p), C.byref(nm), cap)
         return d, m[: nm.value].copy()
 
+    # ------------------------------------------------------------------ refinement (fixed specification, port only)
+    @staticmethod
+    def refine_directions():
+        """sin / cos tables of the 16 interpolation directions, evaluated in float32 (shared by the port and the kernels)."""
+        libm = C.CDLL("libm.so.6")   # the same sinf / cosf the library's host code calls
+        for fn in (libm.sinf, libm.cosf):
+            fn.restype, fn.argtypes = C.c_float, [C.c_float]
+        ang = [np.float32(k) * np.float32(np.pi / 8) for k in range(16)]
+        return (np.array([libm.sinf(C.c_float(a)) for a in ang], np.float32), np.array([libm.cosf(C.c_float(a)) for a in ang], np.float32))
+
+    def refine_region_voting(self, disp, cls, arms, D, ts=20, th=0.4, iters=5):
+        d = np.array(disp, np.float32, order="C")
+        c = np.array(cls, np.uint8, order="C")
+        arms = _c(arms, np.uint8)
+        H, W = d.shape
+        f = self._fn("refine_region_voting")
+        f.restype = None
+        f(_p(d, _f32p), _p(c, _u8p), _p(arms, _u8p), H, W, int(D), int(ts), C.c_float(th), int(iters))
+        return d, c
+
+    def refine_interpolate(self, disp, cls, bgr, max_len):
+        d = np.array(disp, np.float32, order="C")
+        c = np.array(cls, np.uint8, order="C")
+        bgr = _c(bgr, np.uint8)
+        H, W = d.shape
+        sina, cosa = self.refine_directions()
+        f = self._fn("refine_interpolate")
+        f.restype = None
+        f(_p(d, _f32p), _p(c, _u8p), _p(bgr, _u8p), H, W, int(max_len), _p(sina, _f32p), _p(cosa, _f32p))
+        return d, c
+
+    def refine_discontinuity(self, disp, cost, thres=5.0):
+        d = np.array(disp, np.float32, order="C")
+        cost = _c(cost, np.float32)
+        H, W, D = cost.shape
+        f = self._fn("refine_discontinuity")
+        f.restype = None
+        f(_p(d, _f32p), _p(cost, _f32p), H, W, D, C.c_float(thres))
+        return d
+
     def transform_to_show(self, disp):
         """TransformToShow (PostProcessing.h:137)."""
         d = _c(disp, np.float32)

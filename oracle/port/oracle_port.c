@@ -935,3 +935,139 @@ void orc_fill_the_hole_fixed(int row, int col, int dispRange, float* disp, const
                              int32_t* n_mis, int32_t mis_capacity) {
     fill_the_hole_impl(col, row, INFINITY, dispRange, disp, occ, n_occ, mis, n_mis, mis_capacity);
 }
+
+/* ================================================================================================ multi-step refinement
+ * PARITY UNPINNED -- the reference has NO implementation of these steps: only the option fields irv_ts, irv_th and
+ * do_discontinuity_adjustment exist (CBLSM/adcensus_types.h:58-59,65) and nothing reads them.  BASELINE.json's north_star
+ * names "iterative region voting, interpolation and border refinement", so a FIXED SPECIFICATION after Mei et al.,
+ * "On building an accurate stereo matching system on graphics hardware" (2011), sections 2.4, is stated here and the CUDA
+ * path is checked against this restatement only.  Conventions: disparity maps are float [H][W] with +inf = invalid (what
+ * LeftRightConsistency writes, PostProcessing.h:93,131); lists are (row, col) pairs in raster order, as LeftRightConsistency
+ * emits them; arms are CrossAggregator's {left,right,top,bottom} bytes (cross_aggregator.h:17-20).  Every phase reads the map
+ * as it was when the phase (or the voting iteration) began and writes afterwards, so results do not depend on a visiting
+ * order. */
+
+/* Iterative region voting: a listed (invalid) pixel p collects the histogram of the valid disparities in its cross
+ * support region (for each row y+t of p's vertical arm: the horizontal arm span of pixel (y+t, x)), count = their number,
+ * best = the first most frequent disparity; if count > ts and hist[best] / count > th the pixel takes `best` and leaves
+ * its list.  `iters` synchronous iterations.  cls: 0 valid, 1 occlusion, 2 mismatch (raster map of the two lists). */
+void orc_refine_region_voting(float* disp, uint8_t* cls, const uint8_t* arms, int H, int W, int D, int ts, float th, int iters) {
+    float* next = (float*)malloc((size_t)H * W * sizeof(float));
+    int* hist = (int*)malloc((size_t)D * sizeof(int));
+    for (int it = 0; it < iters; ++it) {
+        memcpy(next, disp, (size_t)H * W * sizeof(float));
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                if (!cls[(size_t)y * W + x]) continue;
+                memset(hist, 0, (size_t)D * sizeof(int));
+                int count = 0;
+                const uint8_t* a = arms + ((size_t)y * W + x) * 4;
+                for (int t = -(int)a[2]; t <= (int)a[3]; ++t) {
+                    const int yy = y + t;
+                    if (yy < 0 || yy >= H) continue;
+                    const uint8_t* b = arms + ((size_t)yy * W + x) * 4;
+                    for (int s = -(int)b[0]; s <= (int)b[1]; ++s) {
+                        const int xx = x + s;
+                        if (xx < 0 || xx >= W) continue;
+                        const float d = disp[(size_t)yy * W + xx];
+                        if (d == INFINITY || !(d >= 0.f)) continue;
+                        const int di = (int)lroundf(d);
+                        if (di < 0 || di >= D) continue;
+                        hist[di]++;
+                        count++;
+                    }
+                }
+                if (count <= ts) continue;
+                int best = 0;
+                for (int d = 1; d < D; ++d)
+                    if (hist[d] > hist[best]) best = d;
+                if ((float)hist[best] / (float)count > th) next[(size_t)y * W + x] = (float)best;
+            }
+        for (size_t k = 0; k < (size_t)H * W; ++k)
+            if (cls[k] && next[k] != INFINITY) {
+                disp[k] = next[k];
+                cls[k] = 0;
+            }
+    }
+    free(next);
+    free(hist);
+}
+
+/* Proper interpolation: a listed pixel looks along 16 directions (angle k*pi/8, tables sina/cosa evaluated by the caller in
+ * float) for the first valid disparity, at most max_len - 1 steps, stopping at the image border; an OCCLUSION takes the
+ * smallest disparity found (background), a MISMATCH the disparity of the hit whose BGR colour is closest to its own
+ * (max-channel distance, first direction among equals).  Pixels without any hit stay invalid. */
+void orc_refine_interpolate(float* disp, uint8_t* cls, const uint8_t* bgr, int H, int W, int max_len, const float* sina, const float* cosa) {
+    float* next = (float*)malloc((size_t)H * W * sizeof(float));
+    memcpy(next, disp, (size_t)H * W * sizeof(float));
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const uint8_t c = cls[(size_t)y * W + x];
+            if (!c) continue;
+            float best_d = INFINITY;
+            int best_dist = 1 << 30;
+            const uint8_t* p = bgr + ((size_t)y * W + x) * 3;
+            for (int k = 0; k < 16; ++k)
+                for (int m = 1; m < max_len; ++m) {
+                    const int yy = (int)lroundf((float)y + (float)m * sina[k]);
+                    const int xx = (int)lroundf((float)x + (float)m * cosa[k]);
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) break;
+                    const float d = disp[(size_t)yy * W + xx];
+                    if (d == INFINITY) continue;
+                    if (c == 1) {
+                        if (d < best_d) best_d = d;
+                    } else {
+                        const uint8_t* q = bgr + ((size_t)yy * W + xx) * 3;
+                        int dist = abs((int)p[0] - (int)q[0]);
+                        const int d1 = abs((int)p[1] - (int)q[1]), d2 = abs((int)p[2] - (int)q[2]);
+                        if (d1 > dist) dist = d1;
+                        if (d2 > dist) dist = d2;
+                        if (dist < best_dist) {
+                            best_dist = dist;
+                            best_d = d;
+                        }
+                    }
+                    break;
+                }
+            next[(size_t)y * W + x] = best_d;
+        }
+    for (size_t k = 0; k < (size_t)H * W; ++k)
+        if (cls[k] && next[k] != INFINITY) {
+            disp[k] = next[k];
+            cls[k] = 0;
+        }
+    free(next);
+}
+
+/* Depth-discontinuity adjustment: on an edge pixel of the disparity map (3x3 Sobel, |gx| + |gy| > thres, interior pixels)
+ * with a valid disparity, the disparities of the left and the right neighbour replace it when the aggregated cost volume
+ * rates them lower at this pixel (left first, then right against the better of the two). */
+void orc_refine_discontinuity(float* disp, const float* cost, int H, int W, int D, float thres) {
+    float* next = (float*)malloc((size_t)H * W * sizeof(float));
+    memcpy(next, disp, (size_t)H * W * sizeof(float));
+    for (int y = 1; y < H - 1; ++y)
+        for (int x = 1; x < W - 1; ++x) {
+            const float* r0 = disp + (size_t)(y - 1) * W + x;
+            const float* r1 = disp + (size_t)y * W + x;
+            const float* r2 = disp + (size_t)(y + 1) * W + x;
+            const float gx = ((r0[1] - r0[-1]) + (2.f * r1[1] - 2.f * r1[-1])) + (r2[1] - r2[-1]);
+            const float gy = ((r2[-1] - r0[-1]) + (2.f * r2[0] - 2.f * r0[0])) + (r2[1] - r0[1]);
+            if (!(fabsf(gx) + fabsf(gy) > thres)) continue;
+            const float d = r1[0];
+            if (d == INFINITY || !(d >= 0.f) || lroundf(d) >= D) continue;
+            const float* c = cost + ((size_t)y * W + x) * D;
+            float cbest = c[lroundf(d)], dbest = d;
+            for (int k = 0; k < 2; ++k) {
+                const float d2 = k == 0 ? r1[-1] : r1[1];
+                if (d2 == INFINITY || !(d2 >= 0.f) || lroundf(d2) >= D) continue;
+                const float c2 = c[lroundf(d2)];
+                if (c2 < cbest) {
+                    cbest = c2;
+                    dbest = d2;
+                }
+            }
+            next[(size_t)y * W + x] = dbest;
+        }
+    memcpy(disp, next, (size_t)H * W * sizeof(float));
+    free(next);
+}

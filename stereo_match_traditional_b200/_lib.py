@@ -76,6 +76,10 @@ SIGNATURES = {
     "smt_cross_sweep_info": (_i, [_i, _i, _i32p, _i32p]),
     "smt_aggregate_cross_sweep": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i]),
     "smt_aggregate_fast_status": (_i, [_vp, _i32p]),
+    "smt_invalid_class_map": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i]),
+    "smt_refine_region_voting": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i]),
+    "smt_refine_interpolate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "smt_refine_discontinuity": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _i]),
     "smt_band_create": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "smt_band_destroy": (None, [_vp]),
     "smt_band_geometry": (_i, [_vp, _i32p, _i32p, _i32p, _i32p]),

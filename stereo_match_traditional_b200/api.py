@@ -390,6 +390,45 @@ class Engine:
         self._ck(self.lib.smt_fill_the_hole(self.h, pd, H, W, int(disp_range), po, len(occ), pm, C.byref(nm), 1 if fixed else 0, a.space))
         return d, m[: nm.value]
 
+    # ------------------------------------------------------------------ multi-step refinement (fixed specification)
+    def invalid_class_map(self, occ, mis, shape):
+        """uint8 [H][W]: 0 valid, 1 occlusion, 2 mismatch, from LeftRightConsistency's two (row, col) lists."""
+        H, W = shape
+        occ = np.ascontiguousarray(np.asarray(occ.cpu() if hasattr(occ, "cpu") else occ, np.int32).reshape(-1, 2))
+        mis = np.ascontiguousarray(np.asarray(mis.cpu() if hasattr(mis, "cpu") else mis, np.int32).reshape(-1, 2))
+        a = _Args(self, occ)
+        po = a.inp(occ, np.int32) if len(occ) else None
+        pm = a.inp(mis, np.int32) if len(mis) else None
+        cls, pc = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_invalid_class_map(self.h, po, len(occ), pm, len(mis), H, W, pc, a.space))
+        return cls
+
+    def refine_region_voting(self, disp, cls, arms, D, ts=20, th=0.4, iters=5):
+        a = _Args(self, disp, cls, arms)
+        H, W = disp.shape
+        d, pd = a.out((H, W), np.float32, init=disp)
+        c, pc = a.out((H, W), np.uint8, init=cls)
+        pa = a.inp(arms, np.uint8, (H, W, 4))
+        self._ck(self.lib.smt_refine_region_voting(self.h, pd, pc, pa, H, W, int(D), int(ts), float(th), int(iters), a.space))
+        return d, c
+
+    def refine_interpolate(self, disp, cls, bgr, max_len):
+        a = _Args(self, disp, cls, bgr)
+        H, W = disp.shape
+        d, pd = a.out((H, W), np.float32, init=disp)
+        c, pc = a.out((H, W), np.uint8, init=cls)
+        pb = a.inp(bgr, np.uint8, (H, W, 3))
+        self._ck(self.lib.smt_refine_interpolate(self.h, pd, pc, pb, H, W, int(max_len), a.space))
+        return d, c
+
+    def refine_discontinuity(self, disp, cost, thres=5.0):
+        a = _Args(self, disp, cost)
+        H, W, D = cost.shape
+        d, pd = a.out((H, W), np.float32, init=disp)
+        pc = a.inp(cost, np.float32, (H, W, D))
+        self._ck(self.lib.smt_refine_discontinuity(self.h, pd, pc, H, W, D, float(thres), a.space))
+        return d
+
     def median(self, disp, k=3):
         a = _Args(self, disp)
         H, W = disp.shape
