@@ -349,11 +349,19 @@ typedef struct smt_adcensus_params {
     int32_t speckle_invalid;       /* main.cpp:93 : +inf -> 2147483647    */
     int32_t median_size;           /* main.cpp:94 : 3                     */
     smt_sum_mode_t sum_mode;
+    /* multi-step refinement between the LR check and the speckle filter (see smt_refine_*; NOT part of the reference's
+     * pipeline, all off by default): */
+    int32_t irv_iters;             /* iterative region voting iterations (0 = off; Mei et al. use 5)         */
+    int32_t irv_ts;                /* adcensus_types.h:58 : 20                                               */
+    float irv_th;                  /* adcensus_types.h:59 : 0.4                                              */
+    int32_t do_interpolation;      /* proper interpolation of what region voting left invalid                */
+    int32_t do_discontinuity_adjustment; /* adcensus_types.h:65                                              */
+    float discontinuity_thres;     /* Sobel threshold on the disparity map: 5                                */
 } smt_adcensus_params;
 SMT_API void smt_adcensus_default_params(smt_adcensus_params* p, int32_t rows, int32_t cols, int32_t D);
 /* bgr_*: uint8 [rows][cols][3]; gray_*: uint8 [rows][cols].
  * Outputs (all optional except disp_out), float32 [rows][cols]:
- *   disp_out        after LR check + speckle removal + median
+ *   disp_out        after LR check (+ the optional refinement steps) + speckle removal + median
  *   disp_left_raw   ScanlineOptimizer::WTA of the left view
  *   disp_right_raw  first-min WTA of the aggregated right volume
  *   disp_lrc        left disparity after LeftRightConsistency (+inf = invalidated)

@@ -44,6 +44,8 @@ class AdCensusParams(C.Structure):
         ("speckle_diff", _i), ("speckle_min_area", C.c_uint32), ("speckle_invalid", _i),
         ("median_size", _i),
         ("sum_mode", _i),
+        ("irv_iters", _i), ("irv_ts", _i), ("irv_th", _f),
+        ("do_interpolation", _i), ("do_discontinuity_adjustment", _i), ("discontinuity_thres", _f),
     ]
 
 

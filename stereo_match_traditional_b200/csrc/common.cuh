@@ -266,6 +266,11 @@ smt_status_t k_scanline(smt_ctx* ctx, const float* cost, const float* gray, int 
                         float* left, float* right, float* up, float* down, float* sum, float* disp, float* scratch_a,
                         float* scratch_b);
 smt_status_t k_lrcheck(smt_ctx* ctx, float* dispL, const float* dispR, int W, int H, float gate, bool variant_and,
-                       float* last, int32_t* occ, int32_t* mis, int32_t* counts_dev /*2 ints*/);
+                       float* last, int32_t* occ, int32_t* mis, int32_t* counts_dev /*2 ints*/, uint8_t* cls_out = nullptr);
+// multi-step refinement (refine.cu): cls = 0 valid / 1 occlusion / 2 mismatch
+smt_status_t k_refine_region_voting(smt_ctx* ctx, float* disp, uint8_t* cls, const uint8_t* arms, int H, int W, int D, int ts, float th,
+                                    int iters);
+smt_status_t k_refine_interpolate(smt_ctx* ctx, float* disp, uint8_t* cls, const uint8_t* bgr, int H, int W, int max_len);
+smt_status_t k_refine_discontinuity(smt_ctx* ctx, float* disp, const float* cost, int H, int W, int D, float thres);
 smt_status_t k_remove_speckles(smt_ctx* ctx, float* disp, int W, int H, int diff, uint32_t min_area, int invalid_val);
 smt_status_t k_median(smt_ctx* ctx, const float* in, float* out, int W, int H, int k);

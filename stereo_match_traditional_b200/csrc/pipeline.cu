@@ -27,6 +27,12 @@ extern "C" void smt_adcensus_default_params(smt_adcensus_params* p, int32_t rows
     p->speckle_invalid = 2147483647;  // Invalid_Float bound to `const int&` (main.cpp:93)
     p->median_size = 3;
     p->sum_mode = SMT_SUM_REFERENCE_ORDER;
+    p->irv_iters = 0;  // the refinement steps are not part of the reference's pipeline
+    p->irv_ts = 20;    // adcensus_types.h:73
+    p->irv_th = 0.4f;
+    p->do_interpolation = 0;
+    p->do_discontinuity_adjustment = 0;
+    p->discontinuity_thres = 5.f;
 }
 
 extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcensus_params* p, const uint8_t* bgr_left,
@@ -132,9 +138,16 @@ extern "C" smt_status_t smt_pipeline_adcensus_full(smt_ctx* ctx, const smt_adcen
     // ---- post-processing
     if (d_lraw) SMT_CUDA(ctx, cudaMemcpyAsync(d_lraw, dispL.p, npix * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     if (d_rraw) SMT_CUDA(ctx, cudaMemcpyAsync(d_rraw, dispR.p, npix * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    const bool refine = p->irv_iters > 0 || p->do_interpolation || p->do_discontinuity_adjustment;
+    SMT_ALLOC(ctx, cls, refine ? npix : 0);
     SMT_TRY(k_lrcheck(ctx, dispL.as<float>(), dispR.as<float>(), W, H, (float)p->gate, false, nullptr, nullptr, nullptr,
-                      counts.as<int>()));
+                      counts.as<int>(), refine ? cls.as<uint8_t>() : nullptr));
     if (d_lrc) SMT_CUDA(ctx, cudaMemcpyAsync(d_lrc, dispL.p, npix * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    // ---- optional multi-step refinement (fixed specification, see refine.cu): voting over the left view's support
+    // regions, interpolation along 16 directions, adjustment at disparity edges with the aggregated left volume
+    if (p->irv_iters > 0) SMT_TRY(k_refine_region_voting(ctx, dispL.as<float>(), cls.as<uint8_t>(), aL, H, W, D, p->irv_ts, p->irv_th, p->irv_iters));
+    if (p->do_interpolation) SMT_TRY(k_refine_interpolate(ctx, dispL.as<float>(), cls.as<uint8_t>(), bl, H, W, D));
+    if (p->do_discontinuity_adjustment) SMT_TRY(k_refine_discontinuity(ctx, dispL.as<float>(), res, H, W, D, p->discontinuity_thres));
     SMT_TRY(k_remove_speckles(ctx, dispL.as<float>(), W, H, p->speckle_diff, p->speckle_min_area, p->speckle_invalid));
     SMT_TRY(k_median(ctx, dispL.as<float>(), d_out, W, H, p->median_size));
     {

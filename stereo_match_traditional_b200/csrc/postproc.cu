@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) lr_apply_kernel(const unsigned char* __re
 }
 
 smt_status_t k_lrcheck(smt_ctx* ctx, float* dispL, const float* dispR, int W, int H, float gate, bool variant_and, float* last,
-                       int32_t* occ, int32_t* mis, int32_t* counts_dev) {
+                       int32_t* occ, int32_t* mis, int32_t* counts_dev, uint8_t* cls_out) {
     StageTimer t(ctx, ST_POST);
     const size_t n = (size_t)W * H;
     const int nb = (int)cdiv((long long)n, 256);
@@ -170,6 +170,7 @@ smt_status_t k_lrcheck(smt_ctx* ctx, float* dispL, const float* dispR, int W, in
     SMT_LAUNCH(ctx, lr_count_kernel, nb, 256, 0, cls.as<unsigned char>(), n, bc.as<int>());
     SMT_LAUNCH(ctx, lr_scan_kernel, 1, 1024, 0, bc.as<int>(), nb, counts_dev);
     SMT_LAUNCH(ctx, lr_apply_kernel, nb, 256, 0, cls.as<unsigned char>(), bc.as<int>(), W, H, va, dispL, dispL, last, occ, mis);
+    if (cls_out) SMT_CUDA(ctx, cudaMemcpyAsync(cls_out, cls.p, n, cudaMemcpyDeviceToDevice, ctx->stream));
     return SMT_OK;
 }
 

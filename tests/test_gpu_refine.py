@@ -86,3 +86,23 @@ def test_refinement_device_tensors_and_errors(engine, oracle_port):
     assert np.array_equal(d1.cpu().numpy(), r1) and np.array_equal(c1.cpu().numpy(), k1)
     with pytest.raises(SmtError):
         engine.invalid_class_map(np.array([[H, 0]], np.int32), np.zeros((0, 2), np.int32), (H, W))
+
+
+def test_pipeline_with_refinement_equals_the_composition(engine, oracle_port):
+    """smt_pipeline_adcensus_full with the refinement switches on == LR check -> voting -> interpolation -> adjustment ->
+    RemoveSpeckles -> MedianFilter composed by hand from the port's steps (and is off by default: P_full unchanged)."""
+    H, W, D = 70, 150, 24
+    p, aggL, lrc, occ, mis = _front_end(engine, H, W, D, 321)
+    got = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"], want=("disp", "lrc"), irv_iters=3, irv_ts=2,
+                          irv_th=0.3, do_interpolation=1, do_discontinuity_adjustment=1)
+    assert np.array_equal(got["lrc"], lrc, equal_nan=True)
+    cls = np.zeros((H, W), np.uint8)
+    cls[occ[:, 0], occ[:, 1]] = 1
+    cls[mis[:, 0], mis[:, 1]] = 2
+    d, c = oracle_port.refine_region_voting(lrc, cls, aggL["arms"], D, 2, 0.3, 3)
+    d, c = oracle_port.refine_interpolate(d, c, p["bgr_left"], D)
+    d = oracle_port.refine_discontinuity(d, aggL["cost"], 5.0)
+    want = oracle_port.median(oracle_port.remove_speckles(d, 1, 30, None), 3)
+    assert np.array_equal(got["disp"], want, equal_nan=True)
+    plain = engine.pipeline(p["bgr_left"], p["bgr_right"], D, p["gray_left"], p["gray_right"])
+    assert np.isfinite(got["disp"]).sum() > np.isfinite(plain["disp"][plain["disp"] < 1e9]).sum() - 1
