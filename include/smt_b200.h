@@ -202,6 +202,14 @@ SMT_API smt_status_t smt_band_aggregate_cross(smt_band* band, const uint8_t* arm
                                               const uint16_t* sup_vfirst, int32_t iters, float vmax, smt_sum_mode_t mode);
 SMT_API smt_status_t smt_band_sync(smt_band* band, double* pushed_bytes);
 
+/* CBLSM's main() as one call (CBLSM/CBLSM.cpp:64-67,101-104,133-134,146-153): arm maps of both images (tao 25, 34, 17 in the
+ * reference), ComputeAD / ComputeADRight, costAggregationV5 on (right volume, right arms) and (left volume, left arms), a
+ * second V5 pass on the left volume with the left arms and on the right volume with the LEFT arms again (:150, kept),
+ * ComputeDispOringin on both.  gray_*: uint8 [rows][cols]; disp_*: float32 [rows][cols]. */
+SMT_API smt_status_t smt_pipeline_cblsm(smt_ctx* ctx, const uint8_t* gray_left, const uint8_t* gray_right, int32_t rows,
+                                        int32_t cols, int32_t D, int32_t tao, int32_t max_length, int32_t sec_length,
+                                        smt_sum_mode_t mode, float* disp_left, float* disp_right, smt_memspace_t space);
+
 /* SMT_SUM_FAST evaluates window sums as differences of 32-bit wrap-around fixed-point prefixes (quantum = 2^-25 of the
  * power of two above the largest cost).  That is accurate to 2^-20 per pass as long as every non-zero value entering a
  * window is at least 2^19 quanta; lines that hold a smaller value are redone on compensated float32-pair prefixes, and
@@ -230,6 +238,11 @@ SMT_API smt_status_t smt_aggregate_fast_status(smt_ctx* ctx, int32_t* redone_tas
  *   variant 0: CrossArmAggregation::AggregationVertical (CrossArm.cpp:60)  -- flat slice index, column-major order
  *   variant 1: CrossArmAggregation::Aggregation        (CrossArm.cpp:104) -- flat index, exclusive upper bounds
  *   variant 2: CBLSM costAggregationV5                 (CBLSM/CBLSM.h:1179) -- row-major order
+ *   variant 3: CBLSM costAggregationV4                 (CBLSM/CBLSM.h:1128) -- one arm entry per (pixel, d) CELL: the four arm
+ *              arrays are int32 [rows][cols][D]; exclusive upper bounds, an empty window gives 0/0 = NaN like the
+ *              reference; reference order only (SMT_SUM_FAST falls back to it)
+ * CBLSM costAggregationVertical (CBLSM/CBLSM.h:1227) is variant 0 fed with smt_arms_gray variant-1 maps (same loops, same
+ * column-major order; those arms never leave the image).
  * Returns SMT_ERR_UNSUPPORTED when the arm maps address cells outside the slice (the reference reads out of bounds
  * there).  SMT_SUM_REFERENCE_ORDER is bit-exact; SMT_SUM_FAST uses a double-single summed-area table.
  */
@@ -290,6 +303,14 @@ SMT_API smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32
  * (SAD/Sad.h:96, :141, :15, :40, :22).  Inputs are the replicate-padded grey images [rows_padded][cols_padded],
  * pad = winsize+1 per side (SADmain.cpp:47-48); disp: int32 [rows_padded-2*pad][cols_padded-2*pad] (CV_32S);
  * costs (optional): float32 [..][..][D], the per-disparity SAD vector incl. the copy-previous rule (:125-129).
+ * subpixel (optional, left view only): float32 [..][..], the parabola-refined disparity OptimalDisparity computes and then
+ *   discards (Sad.h:76-84 -- it returns best_disp); 0 wherever the function returns 0.
+ * smt_sad_crosscheck replaces CrossCheckDiaparity on the CV_32S maps (Sad.h:184-221): out int32 [rows][cols] (invalid =
+ *   2147483647, what (int)Invalid_Float is under g++), occ / mis: (row, col) pairs in raster order, capacity rows*cols each.
+ *   The reference indexes right[j - lv] unchecked; the flat element i*cols + j - lv is read whenever it lies inside the map.
+ * smt_ncc_shift replaces ncc() (NCC/NCC.h:117-272), the shifted-image NCC with a clipped 11x11 window and offsets 1..79:
+ *   depth uint8 [rows][cols] = 3 * the best offset (0 if none); right_view selects its "right" branch, add_constant the
+ *   `right += 10` of its last argument.  Needs cols > 79.
  *
  * smt_ncc replaces NCC_algorithem with ComputeCost and WinTakeAll (NCC/NCC.h:69, :15, :53): unpadded grey images
  * [rows][cols]; disp int32 [rows][cols], 0 outside the interior.  costs (optional): float64 [rows][cols][D], the value
@@ -306,7 +327,12 @@ SMT_API smt_status_t smt_median(smt_ctx* ctx, const float* in, float* out, int32
  */
 SMT_API smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded,
                              int32_t cols_padded, int32_t D, int32_t winsize, int32_t right_view, int32_t* disp,
-                             float* costs, smt_memspace_t space);
+                             float* costs, float* subpixel, smt_memspace_t space);
+SMT_API smt_status_t smt_sad_crosscheck(smt_ctx* ctx, const int32_t* disp_left, const int32_t* disp_right, int32_t rows,
+                                        int32_t cols, int32_t* out, int32_t* occ, int32_t* n_occ, int32_t* mis, int32_t* n_mis,
+                                        smt_memspace_t space);
+SMT_API smt_status_t smt_ncc_shift(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols,
+                                   int32_t right_view, int32_t add_constant, uint8_t* depth, smt_memspace_t space);
 SMT_API smt_status_t smt_ncc(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols,
                              int32_t win_size, int32_t D, int32_t* disp, double* costs, smt_memspace_t space);
 SMT_API smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded,

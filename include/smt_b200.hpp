@@ -333,12 +333,12 @@ inline void ComputeDispOringin(float* costVolume, float* disp, int dispRange, in
 inline void GetPointDepthLeft(int32_t* disparity, const ImageView& leftimg, const ImageView& rightimg, const int MaxDisparity, const int winsize,
                               Context& c = Context::Default()) {
     const std::vector<uint8_t> l = leftimg.dense(), r = rightimg.dense();
-    c.check(smt_sad(c.get(), l.data(), r.data(), leftimg.rows, leftimg.cols, MaxDisparity, winsize, 0, disparity, nullptr, SMT_HOST));
+    c.check(smt_sad(c.get(), l.data(), r.data(), leftimg.rows, leftimg.cols, MaxDisparity, winsize, 0, disparity, nullptr, nullptr, SMT_HOST));
 }
 inline void GetPointDepthRight(int32_t* disparity, const ImageView& leftimg, const ImageView& rightimg, const int MaxDisparity, const int winsize,
                                Context& c = Context::Default()) {
     const std::vector<uint8_t> l = leftimg.dense(), r = rightimg.dense();
-    c.check(smt_sad(c.get(), l.data(), r.data(), leftimg.rows, leftimg.cols, MaxDisparity, winsize, 1, disparity, nullptr, SMT_HOST));
+    c.check(smt_sad(c.get(), l.data(), r.data(), leftimg.rows, leftimg.cols, MaxDisparity, winsize, 1, disparity, nullptr, nullptr, SMT_HOST));
 }
 /// disp: int32 [height][width]
 inline void NCC_algorithem(const ImageView& leftImage, const ImageView& rigthImage, const int width, const int height, int32_t* disp, int winSize,

@@ -303,6 +303,15 @@ class Oracle:
         self._fn("cblsm_aggregate_v5")(_p(vol, _f32p), _p(out, _f32p), *[_p(x, _i32p) for x in a], D, H, W)
         return out
 
+    def cblsm_aggregate_variant(self, vol, arms, which):
+        """which = "vertical" (costAggregationVertical, per-pixel arm maps) or "v4" (costAggregationV4, arm VOLUMES [H][W][D])."""
+        vol = _c(vol, np.float32)
+        H, W, D = vol.shape
+        out = np.empty_like(vol)
+        a = [_c(arms[k], np.int32) for k in ("left", "right", "up", "down")]
+        self._fn("cblsm_aggregate_" + which)(_p(vol, _f32p), _p(out, _f32p), *[_p(x, _i32p) for x in a], D, H, W)
+        return out
+
     def cblsm_wta(self, vol):
         vol = _c(vol, np.float32)
         H, W, D = vol.shape
@@ -335,6 +344,33 @@ class Oracle:
         return float(self._fn("sad_optimal_disparity")(_p(s, _f32p), s.shape[0]))
 
     # ------------------------------------------------------------------ NCC
+    def sad_crosscheck(self, dispL, dispR):
+        l, r = _c(dispL, np.int32), _c(dispR, np.int32)
+        H, W = l.shape
+        out = np.empty((H, W), np.int32)
+        occ, mis = np.empty((H * W, 2), np.int32), np.empty((H * W, 2), np.int32)
+        no, nm = C.c_int32(0), C.c_int32(0)
+        f = self._fn("sad_crosscheck")
+        f.restype = None
+        f(_p(l, _i32p), _p(r, _i32p), H, W, _p(out, _i32p), _p(occ, _i32p), C.byref(no), _p(mis, _i32p), C.byref(nm))
+        return out, occ[: no.value].copy(), mis[: nm.value].copy()
+
+    def sad_subpixel(self, sad):
+        """Port only: the value OptimalDisparity computes and discards (Sad.h:76-84)."""
+        sad = _c(sad, np.float32)
+        f = self._fn("sad_subpixel")
+        f.restype = C.c_float
+        return float(f(_p(sad, _f32p), int(sad.size)))
+
+    def ncc_shift(self, left, right, right_view=False, add_constant=False):
+        left, right = _c(left, np.uint8), _c(right, np.uint8)
+        H, W = left.shape
+        out = np.empty((H, W), np.uint8)
+        f = self._fn("ncc_shift")
+        f.restype = None
+        f(_p(left, _u8p), _p(right, _u8p), H, W, int(bool(right_view)), int(bool(add_constant)), _p(out, _u8p))
+        return out
+
     def ncc(self, left, right, D, win_size=10):
         left = _c(left, np.uint8)
         right = _c(right, np.uint8)

@@ -1071,3 +1071,156 @@ void orc_refine_discontinuity(float* disp, const float* cost, int H, int W, int 
     memcpy(disp, next, (size_t)H * W * sizeof(float));
     free(next);
 }
+
+/* ================================================================================================ remaining variants */
+/* costAggregationVertical (CBLSM/CBLSM.h:1227-1272): the same rectangle mean as V5, column-major accumulation */
+void orc_cblsm_aggregate_vertical(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
+                                  const int32_t* armUp, const int32_t* armDown, int D, int H, int W) {
+    const size_t npix = (size_t)H * W;
+    float* layer = (float*)malloc(npix * sizeof(float));
+    for (int d = 0; d < D; ++d) {
+        for (size_t p = 0; p < npix; ++p) layer[p] = vol_in[p * D + d];
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const size_t p = (size_t)i * W + j;
+                float value = 0;
+                int number = 0;
+                for (int a = -armL[p]; a <= armR[p]; ++a)
+                    for (int b = -armUp[p]; b <= armDown[p]; ++b) {
+                        value = value + layer[(long)(i + b) * W + j + a];
+                        ++number;
+                    }
+                vol_out[p * D + d] = value / number;
+            }
+    }
+    free(layer);
+}
+
+/* costAggregationV4 (CBLSM/CBLSM.h:1128-1176): arm arrays per (pixel, d) cell, exclusive upper bounds, row-major;
+ * an empty window divides 0 by 0 */
+void orc_cblsm_aggregate_v4(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR, const int32_t* armUp,
+                            const int32_t* armDown, int D, int H, int W) {
+    const size_t npix = (size_t)H * W;
+    float* layer = (float*)malloc(npix * sizeof(float));
+    for (int d = 0; d < D; ++d) {
+        for (size_t p = 0; p < npix; ++p) layer[p] = vol_in[p * D + d];
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const size_t c = ((size_t)i * W + j) * D + d;
+                float value = 0;
+                int number = 0;
+                for (int b = -armUp[c]; b < armDown[c]; ++b)
+                    for (int a = -armL[c]; a < armR[c]; ++a) {
+                        value = value + layer[(long)(i + b) * W + j + a];
+                        ++number;
+                    }
+                vol_out[c] = value / number;
+            }
+    }
+    free(layer);
+}
+
+/* CrossCheckDiaparity on CV_32S maps (SAD/Sad.h:184-221); right[j - lv] is the flat element i*W + j - lv of a contiguous
+ * Mat (read as 0 where that lies before the buffer, which the reference leaves undefined) */
+void orc_sad_crosscheck(const int32_t* dispL, const int32_t* dispR, int H, int W, int32_t* out, int32_t* occ, int32_t* n_occ,
+                        int32_t* mis, int32_t* n_mis) {
+    int no = 0, nm = 0;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const long p = (long)i * W + j;
+            const int lv = dispL[p];
+            const long q = p - lv;
+            const int rv = (q >= 0 && q < (long)H * W) ? dispR[q] : 0;
+            long diff = (long)lv - (long)rv;
+            if (diff < 0) diff = -diff;
+            if (diff > 5) {
+                if (lv < rv) {
+                    occ[2 * no] = i;
+                    occ[2 * no + 1] = j;
+                    ++no;
+                } else {
+                    mis[2 * nm] = i;
+                    mis[2 * nm + 1] = j;
+                    ++nm;
+                }
+                out[p] = 2147483647; /* (int)Invalid_Float under g++ */
+            } else {
+                out[p] = lv;
+            }
+        }
+    *n_occ = no;
+    *n_mis = nm;
+}
+
+/* the sub-pixel value OptimalDisparity computes and discards (SAD/Sad.h:76-84); 0 where the function returns 0.
+ * NOT observable in the reference (it returns best_disp): a restatement of those lines only. */
+float orc_sad_subpixel(const float* sad, int n) {
+    float minv = 65535.f, best = 65535.f, sec = sad[0];
+    for (int i = 1; i < n; ++i)
+        if (minv > sad[i]) {
+            minv = sad[i];
+            best = (float)i;
+        }
+    for (int i = 0; i < n; ++i)
+        if (minv != sad[i] && sad[i] < sec) sec = sad[i];
+    if (sec - minv <= 0.01) return 0.f;
+    if (best == 0 || best == n - 1) return 0.f;
+    const float c1 = sad[(int)best - 1], c2 = sad[(int)best + 1];
+    float divided = c1 + c2 - 2 * minv;
+    if (divided < 1.f) divided = 1.f;
+    return best + (c1 - c2) / (2 * divided);
+}
+
+/* ncc() (NCC/NCC.h:117-272): shifted image, clipped 11x11 window, the function's own `n`, doubles in its loop order */
+void orc_ncc_shift(const uint8_t* L, const uint8_t* R0, int H, int W, int type_right, int add_constant, uint8_t* depth) {
+    const int max_offset = 79, ks = 5;
+    uint8_t* R = (uint8_t*)malloc((size_t)H * W);
+    uint8_t* tmp = (uint8_t*)malloc((size_t)H * W);
+    double* best = (double*)malloc((size_t)H * W * sizeof(double));
+    for (size_t k = 0; k < (size_t)H * W; ++k) {
+        int v = R0[k] + (add_constant ? 10 : 0);
+        R[k] = (uint8_t)(v > 255 ? 255 : v);
+        best[k] = -2;
+        depth[k] = 0;
+    }
+    for (int off = 1; off <= max_offset; ++off) {
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                if (!type_right) tmp[(size_t)y * W + x] = x < off ? R[(size_t)y * W + x] : R[(size_t)y * W + x - off];
+                else tmp[(size_t)y * W + x] = x < W - off ? L[(size_t)y * W + x + off] : L[(size_t)y * W + x];
+            }
+        const uint8_t* A = type_right ? tmp : L;
+        const uint8_t* B = type_right ? R : tmp;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int sx = x - ks > 0 ? x - ks : 0, sy = y - ks > 0 ? y - ks : 0;
+                const int ex = x + ks < W - 1 ? x + ks : W - 1, ey = y + ks < H - 1 ? y + ks : H - 1;
+                const double n = (double)((ey - sy) * (ex - sx));
+                double ma = 0, mb = 0, sa = 0, sb = 0, num = 0;
+                for (int i = sy; i <= ey; ++i)
+                    for (int j = sx; j <= ex; ++j) {
+                        ma += A[(size_t)i * W + j];
+                        mb += B[(size_t)i * W + j];
+                    }
+                ma /= n;
+                mb /= n;
+                for (int i = sy; i <= ey; ++i)
+                    for (int j = sx; j <= ex; ++j) {
+                        sa += pow(A[(size_t)i * W + j] - ma, 2);
+                        sb += pow(B[(size_t)i * W + j] - mb, 2);
+                        num += (A[(size_t)i * W + j] - ma) * (B[(size_t)i * W + j] - mb);
+                    }
+                num /= n;
+                sa /= n;
+                sb /= n;
+                const double r = num / (sqrt(sa) * sqrt(sb)) / n;
+                if (r > best[(size_t)y * W + x]) {
+                    best[(size_t)y * W + x] = r;
+                    depth[(size_t)y * W + x] = (uint8_t)(off * 3);
+                }
+            }
+    }
+    free(R);
+    free(tmp);
+    free(best);
+}

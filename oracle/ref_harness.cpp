@@ -237,6 +237,18 @@ void ref_cblsm_aggregate_v5(const float* vol_in, float* vol_out, const int32_t* 
     rns_cblsm::costAggregationV5(const_cast<float*>(vol_in), vol_out, const_cast<int*>(armL), const_cast<int*>(armR),
                                  const_cast<int*>(armUp), const_cast<int*>(armDown), D, H, W, 1);
 }
+// dead-code variants of CBLSM.h kept callable for parity of the "remaining variants" row
+void ref_cblsm_aggregate_vertical(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
+                                  const int32_t* armUp, const int32_t* armDown, int D, int H, int W) {
+    rns_cblsm::costAggregationVertical(const_cast<float*>(vol_in), vol_out, const_cast<int*>(armL), const_cast<int*>(armR),
+                                       const_cast<int*>(armUp), const_cast<int*>(armDown), D, H, W, 1);
+}
+// costAggregationV4: the four arm arrays are per (pixel, d) cell, int [H][W][D]
+void ref_cblsm_aggregate_v4(const float* vol_in, float* vol_out, const int32_t* armL, const int32_t* armR,
+                            const int32_t* armUp, const int32_t* armDown, int D, int H, int W) {
+    rns_cblsm::costAggregationV4(const_cast<float*>(vol_in), vol_out, const_cast<int*>(armL), const_cast<int*>(armR),
+                                 const_cast<int*>(armUp), const_cast<int*>(armDown), D, H, W, 1);
+}
 void ref_cblsm_wta(const float* vol, float* disp, int D, int H, int W) {
     rns_cblsm::ComputeDispOringin(const_cast<float*>(vol), disp, D, H, W);
 }
@@ -279,7 +291,27 @@ float ref_sad_optimal_disparity(const float* sad, int D) {
     return rns_sad::OptimalDisparity(v, D);
 }
 
+// CrossCheckDiaparity on CV_32S maps (Sad.h:184-221).  occ / mis: capacity H*W pairs each; returns the counts.
+void ref_sad_crosscheck(const int32_t* dispL, const int32_t* dispR, int H, int W, int32_t* out, int32_t* occ, int32_t* n_occ,
+                        int32_t* mis, int32_t* n_mis) {
+    cv::Mat l(H, W, cv::CV_32SC1, const_cast<int32_t*>(dispL)), r(H, W, cv::CV_32SC1, const_cast<int32_t*>(dispR));
+    cv::Mat o(H, W, cv::CV_32SC1, out);
+    std::vector<std::pair<int, int>> vo, vm;
+    rns_sad::CrossCheckDiaparity(l, r, o, 0, 0, vo, vm);
+    *n_occ = (int32_t)vo.size();
+    *n_mis = (int32_t)vm.size();
+    for (size_t k = 0; k < vo.size(); ++k) { occ[2 * k] = vo[k].first; occ[2 * k + 1] = vo[k].second; }
+    for (size_t k = 0; k < vm.size(); ++k) { mis[2 * k] = vm[k].first; mis[2 * k + 1] = vm[k].second; }
+}
+
 // ---------------------------------------------------------------- NCC (NCC.h)
+// ncc() (NCC.h:117-272), the shifted-image variant; type 0 = "left", 1 = "right"
+void ref_ncc_shift(const uint8_t* L, const uint8_t* R, int H, int W, int type_right, int add_constant, uint8_t* depth) {
+    cv::Mat l = wrap_u8(L, H, W).clone(), r = wrap_u8(R, H, W).clone();
+    cv::Mat d = rns_ncc::ncc(l, r, type_right ? "right" : "left", add_constant != 0);
+    for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) depth[(size_t)i * W + j] = d.at<uchar>(i, j);
+}
+
 // disp CV_32S [H][W], zero-initialised by the caller (NCC_main.cpp:20)
 void ref_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int winSize, int D, int32_t* disp) {
     CoutSilencer q;

@@ -101,7 +101,10 @@ SIGNATURES = {
     "smt_remove_speckles": (_i, [_vp, _vp, _i, _i, _i, C.c_uint32, _i, _i]),
     "smt_median": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "smt_fill_the_hole": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i]),
-    "smt_sad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i]),
+    "smt_sad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
+    "smt_sad_crosscheck": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i32p, _vp, _i32p, _i]),
+    "smt_ncc_shift": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "smt_pipeline_cblsm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i]),
     "smt_ncc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i]),
     "smt_asw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _i, _i, _vp, _vp, _i]),
     "smt_asw_crosscheck": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),

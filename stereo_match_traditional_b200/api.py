@@ -309,11 +309,13 @@ class Engine:
         return res
 
     def aggregate_rect(self, vol, arm_left, arm_right, arm_top, arm_bottom, variant=0, mode=SUM_REFERENCE_ORDER):
-        """variant 0: AggregationVertical, 1: Aggregation (CrossArm.cpp:60,104), 2: costAggregationV5 (CBLSM.h:1179)."""
+        """variant 0: AggregationVertical, 1: Aggregation (CrossArm.cpp:60,104), 2: costAggregationV5 (CBLSM.h:1179),
+        3: costAggregationV4 (CBLSM.h:1128; the four arm arrays are then [H][W][D] volumes)."""
         a = _Args(self, vol, arm_left)
         H, W, D = vol.shape
         pv = a.inp(vol, np.float32)
-        ps = [a.inp(x, np.int32, (H, W)) for x in (arm_left, arm_right, arm_top, arm_bottom)]
+        ashape = (H, W, D) if int(variant) == 3 else (H, W)
+        ps = [a.inp(x, np.int32, ashape) for x in (arm_left, arm_right, arm_top, arm_bottom)]
         out, po = a.out((H, W, D), np.float32)
         self._ck(self.lib.smt_aggregate_rect(self.h, pv, *ps, H, W, D, int(variant), int(mode), po, a.space))
         return out
@@ -438,8 +440,10 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ window matchers
-    def sad(self, left_padded, right_padded, D, winsize=3, right_view=False, want_costs=False):
-        """GetPointDepthLeft / GetPointDepthRight (SAD/Sad.h:96,141) on replicate-padded grey images (pad = winsize+1)."""
+    def sad(self, left_padded, right_padded, D, winsize=3, right_view=False, want_costs=False, want_subpixel=False):
+        """GetPointDepthLeft / GetPointDepthRight (SAD/Sad.h:96,141) on replicate-padded grey images (pad = winsize+1).
+        want_subpixel (left view): also the parabola-refined value OptimalDisparity computes and discards (Sad.h:76-84);
+        the result is then a dict."""
         a = _Args(self, left_padded, right_padded)
         Hp, Wp = left_padded.shape
         pad = winsize + 1
@@ -447,8 +451,45 @@ class Engine:
         pr = a.inp(right_padded, np.uint8, (Hp, Wp))
         disp, pd = a.out((Hp - 2 * pad, Wp - 2 * pad), np.int32)
         costs, pc = a.out((Hp - 2 * pad, Wp - 2 * pad, D), np.float32, want_costs)
-        self._ck(self.lib.smt_sad(self.h, pl, pr, Hp, Wp, D, winsize, int(bool(right_view)), pd, pc, a.space))
+        sub, psub = a.out((Hp - 2 * pad, Wp - 2 * pad), np.float32, want_subpixel)
+        self._ck(self.lib.smt_sad(self.h, pl, pr, Hp, Wp, D, winsize, int(bool(right_view)), pd, pc, psub, a.space))
+        if want_subpixel:
+            return {"disp": disp, "costs": costs, "subpixel": sub}
         return (disp, costs) if want_costs else disp
+
+    def sad_crosscheck(self, disp_left, disp_right):
+        """CrossCheckDiaparity on the CV_32S maps (SAD/Sad.h:184).  Returns (out, occlusions[n,2], mismatches[m,2])."""
+        a = _Args(self, disp_left, disp_right)
+        H, W = disp_left.shape
+        pl = a.inp(disp_left, np.int32, (H, W))
+        pr = a.inp(disp_right, np.int32, (H, W))
+        out, po = a.out((H, W), np.int32)
+        occ, pocc = a.out((H * W, 2), np.int32)
+        mis, pmis = a.out((H * W, 2), np.int32)
+        no, nm = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.smt_sad_crosscheck(self.h, pl, pr, H, W, po, pocc, C.byref(no), pmis, C.byref(nm), a.space))
+        return out, occ[: no.value], mis[: nm.value]
+
+    def ncc_shift(self, left, right, right_view=False, add_constant=False):
+        """ncc() (NCC/NCC.h:117): shifted-image NCC, clipped 11x11 window, offsets 1..79; uint8 depth = 3 * best offset."""
+        a = _Args(self, left, right)
+        H, W = left.shape
+        pl = a.inp(left, np.uint8, (H, W))
+        pr = a.inp(right, np.uint8, (H, W))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_ncc_shift(self.h, pl, pr, H, W, int(bool(right_view)), int(bool(add_constant)), po, a.space))
+        return out
+
+    def pipeline_cblsm(self, gray_left, gray_right, D, tao=25, max_length=34, sec_length=17, mode=SUM_REFERENCE_ORDER):
+        """CBLSM's main() (CBLSM.cpp:64-153) as one call.  Returns (disp_left, disp_right)."""
+        a = _Args(self, gray_left, gray_right)
+        H, W = gray_left.shape
+        pl = a.inp(gray_left, np.uint8, (H, W))
+        pr = a.inp(gray_right, np.uint8, (H, W))
+        dl, pdl = a.out((H, W), np.float32)
+        dr, pdr = a.out((H, W), np.float32)
+        self._ck(self.lib.smt_pipeline_cblsm(self.h, pl, pr, H, W, int(D), int(tao), int(max_length), int(sec_length), int(mode), pdl, pdr, a.space))
+        return dl, dr
 
     def ncc(self, left, right, D, win_size=10, want_costs: bool = False):
         """NCC_algorithem (NCC/NCC.h:69); want_costs adds ComputeCost's value per (pixel, d) as float64 [H][W][D]."""

@@ -267,6 +267,7 @@ smt_status_t k_scanline(smt_ctx* ctx, const float* cost, const float* gray, int 
                         float* scratch_b);
 smt_status_t k_lrcheck(smt_ctx* ctx, float* dispL, const float* dispR, int W, int H, float gate, bool variant_and,
                        float* last, int32_t* occ, int32_t* mis, int32_t* counts_dev /*2 ints*/, uint8_t* cls_out = nullptr);
+smt_status_t k_class_map_to_lists(smt_ctx* ctx, const unsigned char* cls, int W, int H, int32_t* occ, int32_t* mis, int32_t* counts_dev);
 // multi-step refinement (refine.cu): cls = 0 valid / 1 occlusion / 2 mismatch
 smt_status_t k_refine_region_voting(smt_ctx* ctx, float* disp, uint8_t* cls, const uint8_t* arms, int H, int W, int D, int ts, float th,
                                     int iters);

@@ -174,6 +174,17 @@ smt_status_t k_lrcheck(smt_ctx* ctx, float* dispL, const float* dispR, int W, in
     return SMT_OK;
 }
 
+// class map (1 = occlusion, 2 = mismatch) -> the two (row, col) lists in raster order; counts_dev[0..1] = their lengths
+smt_status_t k_class_map_to_lists(smt_ctx* ctx, const unsigned char* cls, int W, int H, int32_t* occ, int32_t* mis, int32_t* counts_dev) {
+    const size_t n = (size_t)W * H;
+    const int nb = (int)cdiv((long long)n, 256);
+    SMT_ALLOC(ctx, bc, (size_t)nb * 2 * sizeof(int));
+    SMT_LAUNCH(ctx, lr_count_kernel, nb, 256, 0, cls, n, bc.as<int>());
+    SMT_LAUNCH(ctx, lr_scan_kernel, 1, 1024, 0, bc.as<int>(), nb, counts_dev);
+    SMT_LAUNCH(ctx, lr_apply_kernel, nb, 256, 0, cls, bc.as<int>(), W, H, 0, (float*)nullptr, (const float*)nullptr, (float*)nullptr, occ, mis);
+    return SMT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- speckles
 // The reference's BFS (:260-310) finds the connected components of the undirected graph {8-neighbours, both valid,
 // |delta| <= diff}; membership does not depend on visiting order, so a lock-free union-find gives the same

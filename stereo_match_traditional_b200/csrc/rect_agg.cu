@@ -143,18 +143,21 @@ static smt_status_t k_arms_gray(smt_ctx* ctx, const uint8_t* img, int ch, int H,
 }
 
 // ---------------------------------------------------------------------------------------------- rectangle aggregation
-enum { RECT_FLAT_COLMAJOR = 0, RECT_FLAT_EXCLUSIVE = 1, RECT_INBOUNDS = 2 };
+enum { RECT_FLAT_COLMAJOR = 0, RECT_FLAT_EXCLUSIVE = 1, RECT_INBOUNDS = 2, RECT_CELL_EXCLUSIVE = 3 };
 
 // bounds of the flat addresses a variant touches; used to refuse shapes for which the reference itself reads out of
 // bounds (memory-safe iff floor((H*H-1)/W)+34 < H-1 for the shipped Right-pass quirk)
 __global__ void __launch_bounds__(256) rect_bounds_kernel(const int* __restrict__ aL, const int* __restrict__ aR,
                                                           const int* __restrict__ aT, const int* __restrict__ aB, int H, int W,
-                                                          int variant, long long* __restrict__ minmax) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= (long long)H * W) return;
+                                                          int variant, int D, long long* __restrict__ minmax) {
+    // RECT_CELL_EXCLUSIVE: one arm entry per (pixel, d) cell (costAggregationV4's arm volumes), otherwise one per pixel
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nent = (long long)H * W * (variant == RECT_CELL_EXCLUSIVE ? D : 1);
+    if (q >= nent) return;
+    const long long p = variant == RECT_CELL_EXCLUSIVE ? q / D : q;
     const int i = (int)(p / W), j = (int)(p % W);
-    const int ex = variant == RECT_FLAT_EXCLUSIVE ? 1 : 0;
-    const int l = aL[p], r = aR[p] - ex, up = aT[p], dn = aB[p] - ex;
+    const int ex = (variant == RECT_FLAT_EXCLUSIVE || variant == RECT_CELL_EXCLUSIVE) ? 1 : 0;
+    const int l = aL[q], r = aR[q] - ex, up = aT[q], dn = aB[q] - ex;
     if (r < -l || dn < -up) return;  // empty window
     long long lo, hi;
     if (variant == RECT_INBOUNDS) {
@@ -178,7 +181,8 @@ __global__ void __launch_bounds__(256) rect_exact_kernel(const float* __restrict
     if (cell >= (size_t)H * W * D) return;
     const size_t pix = cell / D;
     const int d = (int)(cell - pix * D);
-    const int l = aL[pix], r = aR[pix], up = aT[pix], dn = aB[pix];
+    const size_t ai = variant == RECT_CELL_EXCLUSIVE ? cell : pix;
+    const int l = aL[ai], r = aR[ai], up = aT[ai], dn = aB[ai];
     const float* base = in + (long long)pix * D + d;
     float value = 0.f;
     int number = 0;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(256) rect_exact_kernel(const float* __restrict
                 value = __fadd_rn(value, base[((long long)b * W + a) * D]);
                 ++number;
             }
-    } else if (variant == RECT_FLAT_EXCLUSIVE) {  // CrossArm.cpp:131-138
+    } else if (variant == RECT_FLAT_EXCLUSIVE || variant == RECT_CELL_EXCLUSIVE) {  // CrossArm.cpp:131-138, CBLSM.h:1159-1166
         for (int b = -up; b < dn; ++b)
             for (int a = -l; a < r; ++a) {
                 value = __fadd_rn(value, base[((long long)b * W + a) * D]);
@@ -302,7 +306,8 @@ static smt_status_t k_aggregate_rect(smt_ctx* ctx, const float* in, float* out, 
         SMT_ALLOC(ctx, mm, 2 * sizeof(long long));
         const long long init[2] = {0, 0};
         SMT_CUDA(ctx, cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-        SMT_LAUNCH(ctx, rect_bounds_kernel, cdiv((long long)npix, 256), 256, 0, aL, aR, aT, aB, H, W, variant, mm.as<long long>());
+        SMT_LAUNCH(ctx, rect_bounds_kernel, cdiv((long long)(variant == RECT_CELL_EXCLUSIVE ? ncell : npix), 256), 256, 0, aL, aR, aT, aB, H, W,
+                   variant, D, mm.as<long long>());
         long long* h = reinterpret_cast<long long*>(ctx->h_pinned);
         SMT_CUDA(ctx, cudaMemcpyAsync(h, mm.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -312,7 +317,7 @@ static smt_status_t k_aggregate_rect(smt_ctx* ctx, const float* in, float* out, 
                             "of bounds for this shape; CrossArm.cpp:92 is memory-safe only if floor((H*H-1)/W)+34 < H-1)", W, H);
     }
     const unsigned nb = cdiv((long long)ncell, 256);
-    if (mode == SMT_SUM_REFERENCE_ORDER) {
+    if (mode == SMT_SUM_REFERENCE_ORDER || variant == RECT_CELL_EXCLUSIVE) {  // per-cell arms: reference order only
         SMT_LAUNCH(ctx, rect_exact_kernel, nb, 256, 0, in, out, aL, aR, aT, aB, H, W, D, variant);
         return SMT_OK;
     }
@@ -375,20 +380,69 @@ smt_status_t smt_aggregate_rect(smt_ctx* ctx, const float* vol_in, const int32_t
     if (!ctx) return SMT_ERR_INVALID_ARG;
     SMT_REQUIRE(ctx, vol_in && vol_out && arm_left && arm_right && arm_top && arm_bottom && rows > 0 && cols > 0 && D > 0,
                 SMT_ERR_INVALID_ARG, "smt_aggregate_rect: bad argument");
-    SMT_REQUIRE(ctx, variant >= 0 && variant <= 2 && (mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST), SMT_ERR_INVALID_ARG,
+    SMT_REQUIRE(ctx, variant >= 0 && variant <= 3 && (mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST), SMT_ERR_INVALID_ARG,
                 "smt_aggregate_rect: unknown variant or sum mode");
     SMT_REQUIRE(ctx, vol_in != vol_out, SMT_ERR_INVALID_ARG, "smt_aggregate_rect: in-place aggregation is not supported");
     DeviceGuard dev_guard(ctx->device);
     const size_t npix = (size_t)rows * cols;
     Marshal ms(ctx, space);
     const float* din = ms.in(vol_in, npix * D);
-    const int32_t* dL = ms.in(arm_left, npix);
-    const int32_t* dR = ms.in(arm_right, npix);
-    const int32_t* dT = ms.in(arm_top, npix);
-    const int32_t* dB = ms.in(arm_bottom, npix);
+    const size_t narm = variant == RECT_CELL_EXCLUSIVE ? npix * D : npix;
+    const int32_t* dL = ms.in(arm_left, narm);
+    const int32_t* dR = ms.in(arm_right, narm);
+    const int32_t* dT = ms.in(arm_top, narm);
+    const int32_t* dB = ms.in(arm_bottom, narm);
     float* dout = ms.out(vol_out, npix * D);
     SMT_TRY(ms.check());
     SMT_TRY(k_aggregate_rect(ctx, din, dout, dL, dR, dT, dB, rows, cols, D, variant, mode));
+    return ms.finish();
+}
+
+// CBLSM's main() as one call (CBLSM/CBLSM.cpp:64-67, 101-104, 133-134, 146-153): arm maps of both images, AD volumes of both
+// views, costAggregationV5 on (right, right arms), (left, left arms), then a second pass on the left with the left arms
+// and on the right with the LEFT arms again (:150, kept), first-minimum disparities of both views.
+smt_status_t smt_pipeline_cblsm(smt_ctx* ctx, const uint8_t* gray_left, const uint8_t* gray_right, int32_t rows, int32_t cols, int32_t D,
+                                int32_t tao, int32_t max_length, int32_t sec_length, smt_sum_mode_t mode, float* disp_left,
+                                float* disp_right, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, gray_left && gray_right && disp_left && disp_right && rows > 0 && cols > 0 && D > 0, SMT_ERR_INVALID_ARG,
+                "smt_pipeline_cblsm: bad argument");
+    SMT_REQUIRE(ctx, mode == SMT_SUM_REFERENCE_ORDER || mode == SMT_SUM_FAST, SMT_ERR_INVALID_ARG, "smt_pipeline_cblsm: unknown sum mode");
+    DeviceGuard dev_guard(ctx->device);
+    const size_t npix = (size_t)rows * cols, nvol = npix * D;
+    Marshal ms(ctx, space);
+    const uint8_t* gl = ms.in(gray_left, npix);
+    const uint8_t* gr = ms.in(gray_right, npix);
+    float* dl = ms.out(disp_left, npix);
+    float* dr = ms.out(disp_right, npix);
+    SMT_TRY(ms.check());
+    SMT_ALLOC(ctx, arms, 8 * npix * sizeof(int));
+    SMT_ALLOC(ctx, volA, nvol * sizeof(float));
+    SMT_ALLOC(ctx, volB, nvol * sizeof(float));
+    int* aL[4];
+    int* aR[4];
+    for (int k = 0; k < 4; ++k) {
+        aL[k] = arms.as<int>() + (size_t)k * npix;
+        aR[k] = arms.as<int>() + (size_t)(4 + k) * npix;
+    }
+    SMT_TRY(k_arms_gray(ctx, gl, 1, rows, cols, tao, max_length, sec_length, 1, aL[0], aL[1], aL[2], aL[3], nullptr));
+    SMT_TRY(k_arms_gray(ctx, gr, 1, rows, cols, tao, max_length, sec_length, 1, aR[0], aR[1], aR[2], aR[3], nullptr));
+    // right view: ComputeADRight -> V5 (right arms) -> V5 (LEFT arms) -> WTA
+    {
+        StageTimer t(ctx, ST_COST);
+        SMT_LAUNCH(ctx, ad_cost_kernel, cdiv((long long)npix * D, 256), 256, 0, gl, gr, rows, cols, D, 1, volA.as<float>());
+    }
+    SMT_TRY(k_aggregate_rect(ctx, volA.as<float>(), volB.as<float>(), aR[0], aR[1], aR[2], aR[3], rows, cols, D, RECT_INBOUNDS, mode));
+    SMT_TRY(k_aggregate_rect(ctx, volB.as<float>(), volA.as<float>(), aL[0], aL[1], aL[2], aL[3], rows, cols, D, RECT_INBOUNDS, mode));
+    SMT_TRY(k_wta(ctx, volA.as<float>(), rows, cols, D, dr));
+    // left view: ComputeAD -> V5 -> V5 (left arms) -> WTA
+    {
+        StageTimer t(ctx, ST_COST);
+        SMT_LAUNCH(ctx, ad_cost_kernel, cdiv((long long)npix * D, 256), 256, 0, gl, gr, rows, cols, D, 0, volA.as<float>());
+    }
+    SMT_TRY(k_aggregate_rect(ctx, volA.as<float>(), volB.as<float>(), aL[0], aL[1], aL[2], aL[3], rows, cols, D, RECT_INBOUNDS, mode));
+    SMT_TRY(k_aggregate_rect(ctx, volB.as<float>(), volA.as<float>(), aL[0], aL[1], aL[2], aL[3], rows, cols, D, RECT_INBOUNDS, mode));
+    SMT_TRY(k_wta(ctx, volA.as<float>(), rows, cols, D, dl));
     return ms.finish();
 }
 

@@ -86,8 +86,10 @@ static smt_status_t k_box_sum(smt_ctx* ctx, int mode, const uint8_t* A, const ui
 // One thread per output pixel.  Left view: OptimalDisparity (Sad.h:40-85); right view: GetMinSadIndex (:22-38) and
 // the loops that stop one row / column early (:154-160).  costs (optional): float [Ho][Wo][D] with the reference's
 // copy-previous rule for invalid disparities (:125-129).
+// subpix (optional, left view): the value OptimalDisparity computes from the parabola through the winner's neighbours and then
+// discards (Sad.h:76-84: `return best_disp`, not final_disp); 0 wherever the function returns 0.
 __global__ void __launch_bounds__(128) sad_select_kernel(const int* __restrict__ vol, int Ho, int Wo, int D, int right_view,
-                                                         int* __restrict__ disp, float* __restrict__ costs) {
+                                                         int* __restrict__ disp, float* __restrict__ costs, float* __restrict__ subpix) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (size_t)Ho * Wo) return;
     const int io = (int)(p / Wo), jo = (int)(p - (size_t)io * Wo);
@@ -120,6 +122,23 @@ __global__ void __launch_bounds__(128) sad_select_kernel(const int* __restrict__
             result = 0;
         else
             result = (int)best;
+        if (subpix) {
+            float fd = 0.f;
+            if (result != 0) {
+                // sad[] as the reference sees it: invalid disparities repeat the previous value (:125-129)
+                float c1 = 0.f, c2 = 0.f, lastv = 0.f;
+                for (int i = 0; i <= result + 1; ++i) {
+                    const int raw = s[i];
+                    const float v = raw >= 0 ? (float)raw : lastv;
+                    lastv = v;
+                    if (i == result - 1) c1 = v;
+                    if (i == result + 1) c2 = v;
+                }
+                const float divided = fmaxf(1.f, __fsub_rn(__fadd_rn(c1, c2), __fmul_rn(2.f, minv)));   // :81
+                fd = __fadd_rn(best, __fdiv_rn(__fsub_rn(c1, c2), __fmul_rn(2.f, divided)));            // :82
+            }
+            subpix[p] = fd;
+        }
     } else {
         if (io >= Ho - 1 || jo >= Wo - 1) {
             disp[p] = 0;  // never written by the reference: stays Mat::zeros
@@ -395,11 +414,136 @@ __global__ void __launch_bounds__(256) asw_crosscheck_kernel(const float* __rest
     out[p] = fabsf((float)lv - rv) > 5.f ? 0 : (uint8_t)lv;
 }
 
+// ---------------------------------------------------------------------------------------------- SAD cross-check (int maps)
+// CrossCheckDiaparity (SAD/Sad.h:184-221): rv = right[i][j - lv]; |lv - rv| > 5 -> invalid, occlusion if lv < rv else
+// mismatch; the marker written into the CV_32S map is (int)Invalid_Float, 2147483647 under g++.
+// The reference indexes j - lv unchecked; for a contiguous Mat that is the flat element i*cols + j - lv, which is what
+// is read here whenever it lies inside the map (it only leaves it in row 0, where the reference reads before the buffer:
+// those pixels take rv = 0).  Lists come out in raster order through the LR check's compaction kernels.
+__global__ void __launch_bounds__(256) sad_crosscheck_kernel(const int* __restrict__ dl, const int* __restrict__ dr, int H, int W,
+                                                             int* __restrict__ out, unsigned char* __restrict__ cls) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (size_t)H * W) return;
+    const int lv = dl[p];
+    const long long q = (long long)p - lv;
+    const int rv = (q >= 0 && q < (long long)H * W) ? dr[q] : 0;
+    const long long diff = llabs((long long)lv - (long long)rv);
+    unsigned char c = 0;
+    if (diff > 5) {
+        c = lv < rv ? 1 : 2;
+        out[p] = 2147483647;
+    } else {
+        out[p] = lv;
+    }
+    cls[p] = c;
+}
+
+// ---------------------------------------------------------------------------------------------- NCC, shifted-image form
+// ncc() (NCC/NCC.h:117-272): for offsets 1..79 the other image is shifted by the offset (columns that would come from
+// outside keep their own value), an 11x11 window clipped at the image border is correlated, and the offset with the
+// strictly largest score wins (depth = offset * 3 as uchar, 0 if none beats -2).  The function's `n` is
+// (end_y - start_y) * (end_x - start_x), one row and one column short of the window, and is used as the divisor of the
+// means, of the three moments and once more of the score -- reproduced from exact integer window sums:
+// with N taps, S1 = sum a, S2 = sum b, Q1 = sum a^2, Q2 = sum b^2, P = sum ab, ma = S1/n, mb = S2/n:
+//   sum (a-ma)^2 = Q1 - 2 ma S1 + N ma^2,  sum (a-ma)(b-mb) = P - ma S2 - mb S1 + N ma mb.
+__global__ void __launch_bounds__(128) ncc_shift_kernel(const unsigned char* __restrict__ left, const unsigned char* __restrict__ right,
+                                                        int H, int W, int type_right, int add_constant, int max_offset, int ksize,
+                                                        unsigned char* __restrict__ depth) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int sx = max(0, x - ksize), sy = max(0, y - ksize), ex = min(W - 1, x + ksize), ey = min(H - 1, y + ksize);
+    const double n = (double)(ey - sy) * (double)(ex - sx);
+    const double N = (double)(ey - sy + 1) * (double)(ex - sx + 1);
+    double best = -2.0;
+    unsigned char out = 0;
+    for (int off = 1; off <= max_offset; ++off) {
+        long long S1 = 0, S2 = 0, Q1 = 0, Q2 = 0, P = 0;
+        for (int i = sy; i <= ey; ++i)
+            for (int j = sx; j <= ex; ++j) {
+                int a, b;
+                if (!type_right) {  // left: a = left, b = right shifted right by off (`right += 10` saturates like cv::Mat)
+                    a = left[(size_t)i * W + j];
+                    const int jj = j < off ? j : j - off;
+                    b = right[(size_t)i * W + jj];
+                    if (add_constant) b = min(255, b + 10);
+                } else {            // right: a = left shifted left by off, b = right
+                    const int jj = j < W - off ? j + off : j;
+                    a = left[(size_t)i * W + jj];
+                    b = right[(size_t)i * W + j];
+                    if (add_constant) b = min(255, b + 10);
+                }
+                S1 += a;
+                S2 += b;
+                Q1 += a * a;
+                Q2 += b * b;
+                P += a * b;
+            }
+        const double ma = (double)S1 / n, mb = (double)S2 / n;
+        const double va = ((double)Q1 - 2.0 * ma * (double)S1 + N * ma * ma) / n;
+        const double vb = ((double)Q2 - 2.0 * mb * (double)S2 + N * mb * mb) / n;
+        const double num = ((double)P - ma * (double)S2 - mb * (double)S1 + N * ma * mb) / n;
+        const double score = num / (sqrt(va) * sqrt(vb)) / n;
+        if (score > best) {
+            best = score;
+            out = (unsigned char)(off * 3);
+        }
+    }
+    depth[(size_t)y * W + x] = out;
+}
+
 // ---------------------------------------------------------------------------------------------- C ABI
 extern "C" {
 
+smt_status_t smt_sad_crosscheck(smt_ctx* ctx, const int32_t* disp_left, const int32_t* disp_right, int32_t rows, int32_t cols,
+                                int32_t* out, int32_t* occ, int32_t* n_occ, int32_t* mis, int32_t* n_mis, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, disp_left && disp_right && out && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_sad_crosscheck: bad argument");
+    DeviceGuard dev_guard(ctx->device);
+    const size_t n = (size_t)rows * cols;
+    const int nb = (int)cdiv((long long)n, 256);
+    Marshal ms(ctx, space);
+    const int32_t* dl = ms.in(disp_left, n);
+    const int32_t* dr = ms.in(disp_right, n);
+    int32_t* dout = ms.out(out, n);
+    int32_t* docc = ms.out(occ, 2 * n);
+    int32_t* dmis = ms.out(mis, 2 * n);
+    SMT_TRY(ms.check());
+    SMT_ALLOC(ctx, cls, n);
+    SMT_ALLOC(ctx, counts, 2 * sizeof(int));
+    {
+        StageTimer t(ctx, ST_POST);
+        SMT_LAUNCH(ctx, sad_crosscheck_kernel, nb, 256, 0, dl, dr, rows, cols, dout, cls.as<unsigned char>());
+        SMT_TRY(k_class_map_to_lists(ctx, cls.as<unsigned char>(), cols, rows, docc, dmis, counts.as<int>()));
+    }
+    SMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, counts.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_occ) *n_occ = ctx->h_pinned[0];
+    if (n_mis) *n_mis = ctx->h_pinned[1];
+    return ms.finish();
+}
+
+smt_status_t smt_ncc_shift(smt_ctx* ctx, const uint8_t* left, const uint8_t* right, int32_t rows, int32_t cols, int32_t right_view,
+                           int32_t add_constant, uint8_t* depth, smt_memspace_t space) {
+    if (!ctx) return SMT_ERR_INVALID_ARG;
+    SMT_REQUIRE(ctx, left && right && depth && rows > 0 && cols > 0, SMT_ERR_INVALID_ARG, "smt_ncc_shift: bad argument");
+    SMT_REQUIRE(ctx, cols > 79, SMT_ERR_UNSUPPORTED, "smt_ncc_shift: the reference shifts by up to 79 columns and indexes outside narrower images");
+    DeviceGuard dev_guard(ctx->device);
+    const size_t n = (size_t)rows * cols;
+    Marshal ms(ctx, space);
+    const uint8_t* dl = ms.in(left, n);
+    const uint8_t* dr = ms.in(right, n);
+    uint8_t* dd = ms.out(depth, n);
+    SMT_TRY(ms.check());
+    {
+        StageTimer t(ctx, ST_COST);
+        SMT_LAUNCH(ctx, ncc_shift_kernel, dim3(cdiv(cols, 128), rows), 128, 0, dl, dr, rows, cols, right_view ? 1 : 0, add_constant ? 1 : 0, 79, 5,
+                   dd);
+    }
+    return ms.finish();
+}
+
 smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* right_padded, int32_t rows_padded, int32_t cols_padded,
-                     int32_t D, int32_t winsize, int32_t right_view, int32_t* disp, float* costs, smt_memspace_t space) {
+                     int32_t D, int32_t winsize, int32_t right_view, int32_t* disp, float* costs, float* subpixel, smt_memspace_t space) {
     if (!ctx) return SMT_ERR_INVALID_ARG;
     const int w = winsize + 1;
     SMT_REQUIRE(ctx, left_padded && right_padded && disp && D > 0 && winsize >= 0 && rows_padded > 2 * w && cols_padded > 2 * w,
@@ -412,7 +556,9 @@ smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     const uint8_t* dr = ms.in(right_padded, np);
     int32_t* dd = ms.out(disp, no);
     float* dc = ms.out(costs, no * D);
+    float* dsp = ms.out(subpixel, no);
     SMT_TRY(ms.check());
+    SMT_REQUIRE(ctx, !(subpixel && right_view), SMT_ERR_UNSUPPORTED, "smt_sad: the sub-pixel value exists in the left view only (OptimalDisparity)");
     SMT_ALLOC(ctx, vol, no * D * sizeof(int));
     {
         StageTimer t(ctx, ST_COST);
@@ -423,7 +569,7 @@ smt_status_t smt_sad(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     }
     {
         StageTimer t(ctx, ST_WTA);
-        SMT_LAUNCH(ctx, sad_select_kernel, cdiv((long long)no, 128), 128, 0, vol.as<int>(), Ho, Wo, D, right_view ? 1 : 0, dd, dc);
+        SMT_LAUNCH(ctx, sad_select_kernel, cdiv((long long)no, 128), 128, 0, vol.as<int>(), Ho, Wo, D, right_view ? 1 : 0, dd, dc, dsp);
     }
     return ms.finish();
 }
