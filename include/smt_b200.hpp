@@ -324,6 +324,18 @@ inline void costAggregationV5(float* dispvolume, float* CostVolume, int* Armvolu
     c.check(smt_aggregate_rect(c.get(), dispvolume, ArmvolumeL, ArmvolumeR, ArmvolumeUp, ArmvolumeDown, _row_, _col_, dispRange, 2, mode,
                                CostVolume, SMT_HOST));
 }
+/// CBLSM.h:1227 -- the V5 rectangle in column-major order
+inline void costAggregationVertical(float* dispvolume, float* CostVolume, int* ArmvolumeL, int* ArmvolumeR, int* ArmvolumeUp,
+                                    int* ArmvolumeDown, int dispRange, int _row_, int _col_, int /*winSize*/, Context& c = Context::Default()) {
+    c.check(smt_aggregate_rect(c.get(), dispvolume, ArmvolumeL, ArmvolumeR, ArmvolumeUp, ArmvolumeDown, _row_, _col_, dispRange, 0,
+                               SMT_SUM_REFERENCE_ORDER, CostVolume, SMT_HOST));
+}
+/// CBLSM.h:1128 -- the four arm arrays are per (pixel, d) cell, int [row][col][dispRange]
+inline void costAggregationV4(float* dispvolume, float* CostVolume, int* ArmvolumeL, int* ArmvolumeR, int* ArmvolumeUp, int* ArmvolumeDown,
+                              int dispRange, int _row_, int _col_, int /*winSize*/, Context& c = Context::Default()) {
+    c.check(smt_aggregate_rect(c.get(), dispvolume, ArmvolumeL, ArmvolumeR, ArmvolumeUp, ArmvolumeDown, _row_, _col_, dispRange, 3,
+                               SMT_SUM_REFERENCE_ORDER, CostVolume, SMT_HOST));
+}
 inline void ComputeDispOringin(float* costVolume, float* disp, int dispRange, int _row_, int _col_, Context& c = Context::Default()) {
     c.check(smt_wta_first_min(c.get(), costVolume, _row_, _col_, dispRange, disp, SMT_HOST));
 }
@@ -360,6 +372,23 @@ inline void AdaptiveSupportWeightRight(float* disp, const ImageView& leftGray, c
 }
 inline void CrossCheckDiaparity(const float* leftdisp, const float* rightdisp, uint8_t* lastdisp, int rows, int cols, Context& c = Context::Default()) {
     c.check(smt_asw_crosscheck(c.get(), leftdisp, rightdisp, rows, cols, lastdisp, SMT_HOST));
+}
+/// Sad.h:184 -- the CV_32S form; MaxDisparity and winsize are unused by the reference as well
+inline void CrossCheckDiaparity(const int32_t* leftdisp, const int32_t* rightdisp, int32_t* lastdisp, int rows, int cols, const int /*MaxDisparity*/,
+                                const int /*winsize*/, std::vector<std::pair<int, int>>& occlusion, std::vector<std::pair<int, int>>& mismatch,
+                                Context& c = Context::Default()) {
+    std::vector<int32_t> o((size_t)rows * cols * 2), m((size_t)rows * cols * 2);
+    int32_t no = 0, nm = 0;
+    c.check(smt_sad_crosscheck(c.get(), leftdisp, rightdisp, rows, cols, lastdisp, o.data(), &no, m.data(), &nm, SMT_HOST));
+    detail::pairs(o, no, occlusion, true);  // the reference clears both lists first (:193-194)
+    detail::pairs(m, nm, mismatch, true);
+}
+/// NCC.h:117 -- depth: uint8 [rows][cols]
+inline void ncc(const ImageView& in1, const ImageView& in2, const std::string& type, uint8_t* depth, bool add_constant = false,
+                Context& c = Context::Default()) {
+    const std::vector<uint8_t> l = in1.dense(), r = in2.dense();
+    if (type != "left" && type != "right") throw Error(SMT_ERR_INVALID_ARG, "ncc: type must be \"left\" or \"right\"");
+    c.check(smt_ncc_shift(c.get(), l.data(), r.data(), in1.rows, in1.cols, type == "right", add_constant, depth, SMT_HOST));
 }
 
 }  // namespace smt
