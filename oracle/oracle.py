@@ -211,6 +211,53 @@ class Oracle:
         self._fn("fill_the_hole_fixed" if fixed else "fill_the_hole")(row, col, int(disp_range), _p(d, _f32p), _p(o, _i32p), len(o), _p(m, _i32p), C.byref(nm), cap)
         return d, m[: nm.value].copy()
 
+    # ------------------------------------------------------------------ ASW display chain (ASWeight.cpp:66-78)
+    def normalize_minmax_u8_from_u8(self, img):
+        """cv::normalize(img, img, 0, 255, NORM_MINMAX) on CV_8U (port only; pinned to cv2 by tests/golden/display.npz)."""
+        a = _c(img, np.uint8)
+        out = np.empty_like(a)
+        f = self._fn("normalize_minmax_u8_from_u8")
+        f.restype = None
+        f(_p(a, _u8p), a.shape[0], a.shape[1], _p(out, _u8p))
+        return out
+
+    def filter_speckles_u8(self, img, new_val=0, max_size=40, max_diff=2):
+        """cv::filterSpeckles on CV_8UC1 (port only; pinned to cv2)."""
+        a = np.array(img, np.uint8, order="C")
+        f = self._fn("filter_speckles_u8")
+        f.restype = None
+        f(_p(a, _u8p), a.shape[0], a.shape[1], int(new_val), int(max_size), int(max_diff))
+        return a
+
+    def median_blur_u8(self, img, k):
+        """cv::medianBlur on CV_8UC1, ksize 3 / 5 (port only; pinned to cv2)."""
+        a = _c(img, np.uint8)
+        out = np.empty_like(a)
+        f = self._fn("median_blur_u8")
+        f.restype = None
+        f(_p(a, _u8p), _p(out, _u8p), a.shape[0], a.shape[1], int(k))
+        return out
+
+    def fill_image_new(self, img, past_end=0):
+        """FillImageNew (ASW.h:434) as written.  Returns (image, n_unassigned): the last n_unassigned zero pixels of the
+        raster order read past the reference's value vector and must not be compared (the port leaves them 0).
+        past_end: the byte the reference finds one past the image (it reads it)."""
+        a = np.array(img, np.uint8, order="C")
+        H, W = a.shape
+        if self.prefix == "ref_":
+            buf = np.zeros(H * W + 1, np.uint8)
+            buf[:-1] = a.ravel()
+            buf[-1] = past_end
+            f = self._fn("fill_image_new")
+            f.restype = None
+            f(_p(buf, _u8p), H, W)
+            return buf[:-1].reshape(H, W).copy(), None
+        n = C.c_int32(0)
+        f = self._fn("fill_image_new")
+        f.restype = None
+        f(_p(a, _u8p), H, W, int(past_end), C.byref(n))
+        return a, int(n.value)
+
     # ------------------------------------------------------------------ refinement (fixed specification, port only)
     @staticmethod
     def refine_directions():

@@ -1224,3 +1224,135 @@ void orc_ncc_shift(const uint8_t* L, const uint8_t* R0, int H, int W, int type_r
     free(tmp);
     free(best);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The ASW driver's display chain (ASW/ASWeight.cpp:66-78): normalize(lastDisp, 0, 255, NORM_MINMAX) on the 8-bit
+ * cross-checked map, filterSpeckles(lastDisp, 0, 40, 2), medianBlur 5, FillImageNew, medianBlur 3.  Three of these are
+ * OpenCV functions: the sources are not in the reference tree (the project links a prebuilt OpenCV), so they are restated
+ * from OpenCV's published algorithms and pinned by golden vectors made with the cv2 4.13 wheel of the build container
+ * (oracle/make_golden_display.py); FillImageNew is pinned against the compiled reference. */
+
+/* cv::normalize(src, dst, 0, 255, NORM_MINMAX) for CV_8U -> CV_8U: scale = 255 * (1 / (max - min)) in double (0 for a
+ * constant image), shift = -min * scale; convertTo evaluates src * (float)scale + (float)shift in float with ONE rounding
+ * (the SIMD path multiplies and adds fused) and saturate_cast<uchar> rounds half to even. */
+void orc_normalize_minmax_u8_from_u8(const uint8_t* src, int H, int W, uint8_t* out) {
+    const size_t n = (size_t)H * W;
+    int lo = 255, hi = 0;
+    for (size_t k = 0; k < n; ++k) {
+        if (src[k] < lo) lo = src[k];
+        if (src[k] > hi) hi = src[k];
+    }
+    const double scale = 255.0 * ((double)(hi - lo) > 2.220446049250313e-16 ? 1.0 / (double)(hi - lo) : 0.0);
+    const double shift = 0.0 - (double)lo * scale;
+    const float a = (float)scale, b = (float)shift;
+    for (size_t k = 0; k < n; ++k) {
+        const float r = fmaf((float)src[k], a, b);
+        long q = lrintf(r);
+        out[k] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+    }
+}
+
+/* cv::filterSpeckles(img, newVal, maxSpeckleSize, maxDiff) on CV_8UC1 (calib3d): the connected components of the graph
+ * {4-neighbours, both != newVal, |a - b| <= maxDiff}; a component of at most maxSpeckleSize pixels is set to newVal. */
+void orc_filter_speckles_u8(uint8_t* img, int H, int W, int new_val, int max_size, int max_diff) {
+    const size_t n = (size_t)H * W;
+    int32_t* label = (int32_t*)calloc(n, sizeof(int32_t));
+    int32_t* stack = (int32_t*)malloc(n * sizeof(int32_t));
+    uint8_t* small = (uint8_t*)malloc(n + 1);
+    int32_t cur = 0;
+    for (size_t p0 = 0; p0 < n; ++p0) {
+        if (img[p0] == new_val) continue;
+        if (label[p0]) {
+            if (small[label[p0]]) img[p0] = (uint8_t)new_val;
+            continue;
+        }
+        int32_t top = 0, count = 0;
+        stack[top++] = (int32_t)p0;
+        label[p0] = ++cur;
+        while (top) {
+            const int32_t p = stack[--top];
+            const int i = p / W, j = p - i * W;
+            const int v = img[p];
+            ++count;
+            const int32_t nb[4] = {j + 1 < W ? p + 1 : -1, j > 0 ? p - 1 : -1, i + 1 < H ? p + W : -1, i > 0 ? p - W : -1};
+            for (int t = 0; t < 4; ++t) {
+                const int32_t q = nb[t];
+                if (q < 0 || label[q] || img[q] == new_val || abs(v - (int)img[q]) > max_diff) continue;
+                label[q] = cur;
+                stack[top++] = q;
+            }
+        }
+        /* pixels of a small component that were already set to newVal are skipped above by the first test; the values
+         * read by the flood fill of LATER components are therefore the modified ones, as in OpenCV -- it makes no
+         * difference, a pixel equal to newVal is never an edge endpoint either way */
+        small[cur] = count <= max_size;
+        if (small[cur]) img[p0] = (uint8_t)new_val;
+    }
+    free(label);
+    free(stack);
+    free(small);
+}
+
+/* cv::medianBlur on CV_8UC1, ksize 3 or 5: the median of the k*k window with BORDER_REPLICATE. */
+void orc_median_blur_u8(const uint8_t* in, uint8_t* out, int H, int W, int k) {
+    const int r = k / 2;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            int hist[256] = {0};
+            for (int di = -r; di <= r; ++di)
+                for (int dj = -r; dj <= r; ++dj) {
+                    const int y = i + di < 0 ? 0 : i + di >= H ? H - 1 : i + di;
+                    const int x = j + dj < 0 ? 0 : j + dj >= W ? W - 1 : j + dj;
+                    ++hist[in[(size_t)y * W + x]];
+                }
+            int acc = 0, v = 0;
+            while ((acc += hist[v]) <= k * k / 2) ++v;
+            out[(size_t)i * W + j] = (uint8_t)v;
+        }
+}
+
+/* FillImageNew (ASW/ASW.h:434-511) as written.  Every zero pixel, in raster order and reading the UNMODIFIED image:
+ *   to the left it probes columns c, c-1, c-3, c-6, ... (the offset grows AND accumulates, :468, :483) and takes the first
+ *   non-zero value; if that runs off the row, to the right c, c+1, c+3, ... where column == cols is still read (:489 tests
+ *   `> col`): that is the first pixel of the next row, and `past_end` for the last row.  Running beyond pushes 0; ending
+ *   exactly on column == cols with a zero there pushes NOTHING (:485 leaves the loop), so from then on pixel i receives
+ *   the value found for a later pixel (:503-509 pairs the two vectors by index) and the last pixels read beyond the value
+ *   vector -- those are left untouched here and reported through n_unassigned. */
+void orc_fill_image_new(uint8_t* disp, int H, int W, int past_end, int32_t* n_unassigned) {
+    const size_t n = (size_t)H * W;
+    int32_t* vals = (int32_t*)malloc((n + 1) * sizeof(int32_t));
+    size_t nv = 0, nz = 0;
+    for (size_t p = 0; p < n; ++p) {
+        if (disp[p]) continue;
+        ++nz;
+        const int i = (int)(p / W), c = (int)(p - (size_t)i * W);
+        const uint8_t* row = disp + (size_t)i * W;
+        int found = -1;
+        for (int col = c, off = 0; col >= 0; ++off, col -= off)
+            if (row[col]) { found = row[col]; break; }
+        if (found < 0) {
+            int col = c, off = 0, pushed = 0;
+            while (col < W) {
+                col += off;
+                if (col > W) { found = 0; pushed = 1; break; }
+                const int v = (col == W && i == H - 1) ? past_end : row[col];
+                if (v) { found = v; pushed = 1; break; }
+                ++off;
+            }
+            if (!pushed) continue;
+        }
+        vals[nv++] = found;
+    }
+    /* the image is written only now, after every search (:503-509); walk a snapshot of the zero mask */
+    uint8_t* zero = (uint8_t*)malloc(n);
+    for (size_t p = 0; p < n; ++p) zero[p] = disp[p] == 0;
+    size_t k = 0;
+    for (size_t p = 0; p < n; ++p) {
+        if (!zero[p]) continue;
+        if (k < nv) disp[p] = (uint8_t)vals[k];
+        ++k;
+    }
+    if (n_unassigned) *n_unassigned = (int32_t)(nz - nv);
+    free(zero);
+    free(vals);
+}

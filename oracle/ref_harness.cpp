@@ -412,5 +412,14 @@ void ref_asw_crosscheck(const float* dispL, const float* dispR, int H, int W, ui
     cv::Mat o(H, W, cv::CV_8UC1, out);
     rns_asw::CrossCheckDiaparity(l, r, o, 0, 3);
 }
+// FillImageNew (ASW/ASW.h:434), the hole filling of the ASW driver's display chain (ASWeight.cpp:76).  The function reads
+// disp.at<uchar>(row, cols) -- one element past the row, for the last row one byte past the image (:494) -- so the caller
+// hands in rows*cols + 1 bytes and decides what that byte holds.  n_values: how many fill values the reference collected
+// (when a search ends exactly on that element with a zero in it, :485-500 pushes nothing and every later pixel takes its
+// successor's value; the last pixels then read past the end of the value vector, which the caller must not compare).
+void ref_fill_image_new(uint8_t* disp_plus1, int H, int W) {
+    cv::Mat d(H, W, cv::CV_8UC1, disp_plus1);
+    rns_asw::FillImageNew(d);
+}
 
 }  // extern "C"

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
                                                     
                                                      const uchar4* __restrict__ arms, const uint16_t* __restrict__ sup, int H, int W,
                                                      int D, int horiz, float bias, float2* __restrict__ wta_partial, int zero, int tmaps,
-                                                     const int* __restrict__ redo, int st_lo, int st_hi) {
+                                                     const int* __restrict__ redo, int nseg, int st_lo, int st_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_ring = smem_raw + (size_t)warp * SEQ_SMEM_PER_WARP;  // [slot][lane] float2
@@ -314,30 +314,37 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
     __shared__ Desc s_desc_all[SEQ_WARPS][SEQ_CH];
     Desc* s_desc = s_desc_all[warp];
     const int nchunk = (D + 31) >> 5;
-    long long wg = (long long)blockIdx.x * SEQ_WARPS + warp;
+    const int len = horiz ? W : H;
+    const int st_lo0 = st_lo, st_hi0 = st_hi;
     // redo != nullptr: this launch is queued behind a fixed-point sweep (cross_agg_fx.cu) and only redoes the (line, chunk)
-    // tasks that sweep put on its list -- or every task once the sweep escalated
-    // A listed line is cut into gridDim.y segments walked by different warps: a handful of warps each walking a whole line
+    // tasks that sweep put on its list -- or every task once the sweep escalated.  The host does not know how many there
+    // are, so a redo launch is a small fixed grid whose warps stride over the list (a full grid of ~17 000 blocks that
+    // return at once costs more than the walks themselves); any other launch has one warp per task and leaves the loop
+    // after its first round.
+    // A listed line is cut into nseg segments walked by different warps: a handful of warps each walking a whole line
     // would leave the launch bound by the latency of one walk (~50 us at 1920 positions).  A segment starts its prefix
     // 48 positions early (outputs only read prefix entries up to 34 positions back) and stores its own positions only.
     // Not for in-place launches (in == out): a segment's lead-in would read what its neighbour has already overwritten.
+    const bool listed = redo && *reinterpret_cast<const volatile int*>(redo + FX_ST_ESCALATED) == 0;
+    const long long nlisted = listed ? (long long)*reinterpret_cast<const volatile int*>(redo + FX_ST_COUNT) * nseg : 0;
+    for (long long v = (long long)blockIdx.x * SEQ_WARPS + warp;; v += (long long)gridDim.x * SEQ_WARPS) {
+    long long wg = v;
     int seg_lo = 0, seg_hi = 0x7fffffff;
-    if (redo && *reinterpret_cast<const volatile int*>(redo + FX_ST_ESCALATED) == 0) {
-        if (wg >= *reinterpret_cast<const volatile int*>(redo + FX_ST_COUNT)) return;
-        wg = redo[FX_ST_LIST + wg];
-        if (gridDim.y > 1) {
-            const int seg_len = ((horiz ? W : H) + (int)gridDim.y - 1) / (int)gridDim.y;
-            seg_lo = (int)blockIdx.y * seg_len;
+    if (listed) {
+        if (v >= nlisted) break;
+        const long long idx = v / nseg;
+        wg = redo[FX_ST_LIST + idx];
+        if (nseg > 1) {
+            const int seg_len = (len + nseg - 1) / nseg;
+            seg_lo = (int)(v - idx * nseg) * seg_len;
             seg_hi = seg_lo + seg_len;
         }
-    } else if (blockIdx.y > 0) {
-        return;  // whole sweeps are walked line by line
     }
     const int line = (int)(wg / nchunk), chunk = (int)(wg - (long long)line * nchunk);
-    const int len = horiz ? W : H;
-    if (line >= (horiz ? H : W) || seg_lo >= len) return;  // whole warp; warps never synchronise with each other
-    st_lo = max(st_lo, seg_lo);
-    st_hi = min(st_hi, seg_hi);
+    if (line >= (horiz ? H : W)) break;  // whole warp; warps never synchronise with each other
+    if (seg_lo >= len) continue;
+    st_lo = max(st_lo0, seg_lo);
+    st_hi = min(st_hi0, seg_hi);
     const int o_first = max(0, (seg_lo - 48) / SEQ_CH);                                      // first chunk walked
     const int o_last = seg_hi >= len ? 0x7fffffff : (seg_hi + SEQ_LOOK + SEQ_CH - 1) / SEQ_CH;  // one past the last
     const int d = chunk * 32 + lane;
@@ -395,6 +402,7 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
         SMT_SEQ_STEP(vb, va)
 #endif
     }
+    }
 #undef SMT_SEQ_STEP
 }
 
@@ -403,7 +411,10 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
                                int horiz, float bias, float2* wta_partial = nullptr, int tmaps = 0, const int* redo = nullptr, int st_lo = 0,
                                int st_hi = 0) {
     // redo launches that do not run in place cut the listed lines into segments (see the kernel)
-    const unsigned nseg = (redo && in != out) ? (unsigned)max(1, min(8, (horiz ? W : H) / 192)) : 1u;
+#ifndef SMT_REDO_SEGS
+#define SMT_REDO_SEGS 8
+#endif
+    const int nseg = (redo && in != out) ? max(1, min(SMT_REDO_SEGS, (horiz ? W : H) / 192)) : 1;
     if (st_hi <= 0) {
         st_lo = 0;
         st_hi = horiz ? W : H;
@@ -418,7 +429,8 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
                                            (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    if (redo) nwarps = min(nwarps, (long long)ctx->sm_count * SEQ_CTAS_PER_SM * SEQ_WARPS);  // the warps stride over the list
     // horizontal walk of a 256-disparity volume (the benchmark shape): the position step is a compile-time constant, so
     // the 32 loads and 32 stores of a chunk use immediate offsets from one base register (-27 % instructions, +1.3 %)
     if constexpr (NONNEG && !WTA) if (horiz && D == 256) {
@@ -430,12 +442,12 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
                                                (int)cudaSharedmemCarveoutMaxShared));
             attr2 = true;
         }
-        SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), dim3(cdiv(nwarps, SEQ_WARPS), nseg), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
-                   horiz, bias, wta_partial, 0, tmaps, redo, st_lo, st_hi);
+        SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA, 256>), dim3(cdiv(nwarps, SEQ_WARPS)), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D,
+                   horiz, bias, wta_partial, 0, tmaps, redo, nseg, st_lo, st_hi);
         return SMT_OK;
     }
-    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), dim3(cdiv(nwarps, SEQ_WARPS), nseg), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
-               bias, wta_partial, 0, tmaps, redo, st_lo, st_hi);
+    SMT_LAUNCH(ctx, (agg_seq_kernel<NONNEG, HAS_SUP, WTA>), dim3(cdiv(nwarps, SEQ_WARPS)), SEQ_WARPS * 32, smem, in, out, arms, sup, H, W, D, horiz,
+               bias, wta_partial, 0, tmaps, redo, nseg, st_lo, st_hi);
     return SMT_OK;
 }
 
