@@ -358,6 +358,33 @@ SMT_API smt_status_t smt_transform_to_show(smt_ctx* ctx, const float* disp, int3
                                            smt_memspace_t space);
 SMT_API smt_status_t smt_normalize_minmax_u8(smt_ctx* ctx, const float* src, int32_t rows, int32_t cols, uint8_t* out,
                                              smt_memspace_t space);
+/* The ASW driver's display chain on the 8-bit cross-checked map (ASW/ASWeight.cpp:66-78).  normalize, filterSpeckles and
+ * medianBlur are OpenCV functions (the reference links a prebuilt OpenCV; no sources in its tree): they follow OpenCV's
+ * behaviour and are pinned to cv2 4.13 by tests/golden/display.npz.
+ *   smt_normalize_minmax_u8_from_u8   normalize(m, m, 0, 255, NORM_MINMAX) on CV_8U (+ the no-op convertTo)   :69, :72
+ *   smt_filter_speckles_u8            cv::filterSpeckles(m, newVal, maxSpeckleSize, maxDiff) on CV_8UC1        :73
+ *                                     (4-connected components of |a-b| <= maxDiff among pixels != newVal; <= size -> newVal)
+ *   smt_median_blur_u8                cv::medianBlur(m, m, ksize), ksize 3 or 5, BORDER_REPLICATE              :74, :78
+ *   smt_fill_image_new                FillImageNew (ASW/ASW.h:434) AS WRITTEN: a zero pixel takes the first non-zero value
+ *                                     at columns c-1, c-3, c-6, ... else at c+1, c+3, ...; the reference also reads column
+ *                                     == cols (the next row's first pixel; below the last row one byte past the image,
+ *                                     which the caller supplies as past_end) and, when a search ends exactly there on a
+ *                                     zero, records no value, which shifts the values of all later pixels by one.  The
+ *                                     last n_unassigned zero pixels (host pointer, optional) read past the reference's
+ *                                     value vector; they are left 0 here.  cols <= 65535.
+ *   smt_asw_display_chain             everything after the two matcher calls: CrossCheckDiaparity, the four steps above
+ *                                     with the reference's constants (0, 40, 2; 5; 3); outputs are the three images the
+ *                                     driver writes ("speckle.png", "filled.png", "medain.png"), the first two optional */
+SMT_API smt_status_t smt_normalize_minmax_u8_from_u8(smt_ctx* ctx, const uint8_t* src, int32_t rows, int32_t cols, uint8_t* out,
+                                                     smt_memspace_t space);
+SMT_API smt_status_t smt_filter_speckles_u8(smt_ctx* ctx, uint8_t* img, int32_t rows, int32_t cols, int32_t new_val,
+                                            int32_t max_speckle_size, int32_t max_diff, smt_memspace_t space);
+SMT_API smt_status_t smt_median_blur_u8(smt_ctx* ctx, const uint8_t* in, uint8_t* out, int32_t rows, int32_t cols, int32_t ksize,
+                                        smt_memspace_t space);
+SMT_API smt_status_t smt_fill_image_new(smt_ctx* ctx, uint8_t* disp, int32_t rows, int32_t cols, int32_t past_end,
+                                        int32_t* n_unassigned, smt_memspace_t space);
+SMT_API smt_status_t smt_asw_display_chain(smt_ctx* ctx, const float* disp_left, const float* disp_right, int32_t rows, int32_t cols,
+                                           uint8_t* speckle_img, uint8_t* filled_img, uint8_t* median_img, smt_memspace_t space);
 
 /* ------------------------------------------------------------------------------------------------ full pipeline
  * P_full: the composition of the reference entry points above with the reference's own

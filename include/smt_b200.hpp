@@ -390,6 +390,25 @@ inline void ncc(const ImageView& in1, const ImageView& in2, const std::string& t
     if (type != "left" && type != "right") throw Error(SMT_ERR_INVALID_ARG, "ncc: type must be \"left\" or \"right\"");
     c.check(smt_ncc_shift(c.get(), l.data(), r.data(), in1.rows, in1.cols, type == "right", add_constant, depth, SMT_HOST));
 }
+/// ASW.h:434 -- in place on an 8-bit map (rows x cols, dense); the byte the reference reads below the last row counts as 0
+inline void FillImageNew(uint8_t* disp, int rows, int cols, Context& c = Context::Default()) {
+    c.check(smt_fill_image_new(c.get(), disp, rows, cols, 0, nullptr, SMT_HOST));
+}
+/// the OpenCV calls of the ASW driver's display chain (ASWeight.cpp:69-78) on dense 8-bit maps
+inline void normalize(const uint8_t* src, uint8_t* dst, int rows, int cols, Context& c = Context::Default()) {  // (0, 255, NORM_MINMAX)
+    c.check(smt_normalize_minmax_u8_from_u8(c.get(), src, rows, cols, dst, SMT_HOST));
+}
+inline void filterSpeckles(uint8_t* img, int rows, int cols, double newVal, int maxSpeckleSize, double maxDiff, Context& c = Context::Default()) {
+    c.check(smt_filter_speckles_u8(c.get(), img, rows, cols, (int32_t)newVal, maxSpeckleSize, (int32_t)maxDiff, SMT_HOST));
+}
+inline void medianBlur(const uint8_t* src, uint8_t* dst, int rows, int cols, int ksize, Context& c = Context::Default()) {
+    if (src == dst) {  // OpenCV allows in-place use (ASWeight.cpp:74)
+        std::vector<uint8_t> tmp(src, src + (size_t)rows * cols);
+        c.check(smt_median_blur_u8(c.get(), tmp.data(), dst, rows, cols, ksize, SMT_HOST));
+        return;
+    }
+    c.check(smt_median_blur_u8(c.get(), src, dst, rows, cols, ksize, SMT_HOST));
+}
 
 }  // namespace smt
 #endif  // SMT_B200_HPP_

@@ -113,6 +113,11 @@ SIGNATURES = {
     "smt_u8_to_f32": (_i, [_vp, _vp, C.c_size_t, _vp, _i]),
     "smt_transform_to_show": (_i, [_vp, _vp, _i, _i, _vp, _i]),
     "smt_normalize_minmax_u8": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "smt_normalize_minmax_u8_from_u8": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "smt_filter_speckles_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "smt_median_blur_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
+    "smt_fill_image_new": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i]),
+    "smt_asw_display_chain": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
     "smt_adcensus_default_params": (None, [C.POINTER(AdCensusParams), _i, _i, _i]),
     "smt_pipeline_adcensus_full": (_i, [_vp, C.POINTER(AdCensusParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
 }

@@ -566,6 +566,53 @@ class Engine:
         self._ck(self.lib.smt_normalize_minmax_u8(self.h, pi, H, W, po, a.space))
         return out
 
+    # ------------------------------------------------------------------ the ASW driver's display chain (ASWeight.cpp:66-78)
+    def normalize_minmax_u8_from_u8(self, src):
+        a = _Args(self, src)
+        H, W = src.shape
+        pi = a.inp(src, np.uint8, (H, W))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_normalize_minmax_u8_from_u8(self.h, pi, H, W, po, a.space))
+        return out
+
+    def filter_speckles_u8(self, img, new_val=0, max_speckle_size=40, max_diff=2):
+        """cv::filterSpeckles on an 8-bit map; returns the filtered copy."""
+        a = _Args(self, img)
+        H, W = img.shape
+        out, po = a.out((H, W), np.uint8, init=img)
+        self._ck(self.lib.smt_filter_speckles_u8(self.h, po, H, W, int(new_val), int(max_speckle_size), int(max_diff), a.space))
+        return out
+
+    def median_blur_u8(self, img, ksize):
+        a = _Args(self, img)
+        H, W = img.shape
+        pi = a.inp(img, np.uint8, (H, W))
+        out, po = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_median_blur_u8(self.h, pi, po, H, W, int(ksize), a.space))
+        return out
+
+    def fill_image_new(self, img, past_end=0):
+        """FillImageNew (ASW.h:434) as written.  Returns (image, n_unassigned)."""
+        a = _Args(self, img)
+        H, W = img.shape
+        out, po = a.out((H, W), np.uint8, init=img)
+        n = C.c_int32(0)
+        self._ck(self.lib.smt_fill_image_new(self.h, po, H, W, int(past_end), C.byref(n), a.space))
+        return out, int(n.value)
+
+    def asw_display_chain(self, disp_left, disp_right):
+        """Cross-check, normalize, filterSpeckles(0, 40, 2), medianBlur 5, FillImageNew, medianBlur 3.
+        Returns the three images the driver writes: (speckle, filled, median)."""
+        a = _Args(self, disp_left, disp_right)
+        H, W = disp_left.shape
+        pl = a.inp(disp_left, np.float32, (H, W))
+        pr = a.inp(disp_right, np.float32, (H, W))
+        o1, p1 = a.out((H, W), np.uint8)
+        o2, p2 = a.out((H, W), np.uint8)
+        o3, p3 = a.out((H, W), np.uint8)
+        self._ck(self.lib.smt_asw_display_chain(self.h, pl, pr, H, W, p1, p2, p3, a.space))
+        return o1, o2, o3
+
     # ------------------------------------------------------------------ full pipeline
     def default_params(self, H, W, D) -> AdCensusParams:
         p = AdCensusParams()

@@ -219,6 +219,7 @@ struct Marshal {
 
 // ---- internal device-pointer entry points shared between translation units (all enqueue on ctx->stream) ----
 smt_status_t k_f32_to_u8(smt_ctx* ctx, const float* in, size_t n, uint8_t* out);  // validates 0..255 integers
+smt_status_t k_asw_crosscheck(smt_ctx* ctx, const float* dl, const float* dr, int H, int W, uint8_t* out);  // window_match.cu
 smt_status_t k_u8_to_f32(smt_ctx* ctx, const uint8_t* in, size_t n, float* out);
 smt_status_t k_bgr_to_gray(smt_ctx* ctx, const uint8_t* bgr, size_t n, uint8_t* gray);
 smt_status_t k_ensure_lut(smt_ctx* ctx, float sigmaC, float sigmaS);

@@ -5,6 +5,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "unionfind.cuh"
 
 // ---------------------------------------------------------------------------------------------- LR check
 // The reference walks pixels in row-major order and invalidates IN PLACE, so the occlusion/mismatch test of a later
@@ -189,33 +190,6 @@ smt_status_t k_class_map_to_lists(smt_ctx* ctx, const unsigned char* cls, int W,
 // The reference's BFS (:260-310) finds the connected components of the undirected graph {8-neighbours, both valid,
 // |delta| <= diff}; membership does not depend on visiting order, so a lock-free union-find gives the same
 // components.  Components smaller than min_area are overwritten with (float)invalid_val.
-__device__ __forceinline__ int uf_find(volatile int* L, int a) {
-    int b = L[a];
-    while (b != a) {
-        a = b;
-        b = L[a];
-    }
-    return a;
-}
-__device__ __forceinline__ void uf_union(int* L, int a, int b) {
-    bool done;
-    do {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
-        if (a < b) {
-            int old = atomicMin(&L[b], a);
-            done = (old == b);
-            b = old;
-        } else if (b < a) {
-            int old = atomicMin(&L[a], b);
-            done = (old == a);
-            a = old;
-        } else {
-            done = true;
-        }
-    } while (!done);
-}
-
 // edge predicate of the reference's region growing (:290-292): both valid, |delta| <= diff
 __device__ __forceinline__ bool spk_conn(float a, float b, float invalid, float diff) {
     return a != invalid && b != invalid && fabsf(a - b) <= diff;
@@ -278,17 +252,6 @@ __global__ void __launch_bounds__(256) spk_merge_kernel(const float* __restrict_
     if (c_se && !(c_s && spk_conn(ss, se, invalid, diff)) && !(c_r && spk_conn(vr, se, invalid, diff)))
         uf_union(label, (int)p, (int)(q + 1));
 }
-__global__ void __launch_bounds__(256) spk_count_kernel(int* __restrict__ label, size_t n, int* __restrict__ size) {
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int root = -1;
-    if (p < n && label[p] >= 0) {
-        root = uf_find(label, (int)p);
-        label[p] = root;  // roots keep label[root]==root, so concurrent finds stay valid
-    }
-    // one atomic per distinct root per warp (large regions would otherwise serialise on a single address)
-    const unsigned peers = __match_any_sync(0xffffffffu, root);
-    if (root >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&size[root], __popc(peers));
-}
 __global__ void __launch_bounds__(256) spk_apply_kernel(const int* __restrict__ label, const int* __restrict__ size, size_t n,
                                                         unsigned min_area, float invalid, float* __restrict__ disp) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +273,7 @@ smt_status_t k_remove_speckles(smt_ctx* ctx, float* disp, int W, int H, int diff
         SMT_CUDA(ctx, cudaFuncSetAttribute(spk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W * sizeof(int))));
     SMT_LAUNCH(ctx, spk_rows_kernel, H, 256, (size_t)W * sizeof(int), disp, W, inv, (float)diff, label.as<int>(), size.as<int>());
     SMT_LAUNCH(ctx, spk_merge_kernel, nb, 256, 0, disp, W, H, inv, (float)diff, label.as<int>());
-    SMT_LAUNCH(ctx, spk_count_kernel, nb, 256, 0, label.as<int>(), n, size.as<int>());
+    SMT_LAUNCH(ctx, uf_count_kernel, nb, 256, 0, label.as<int>(), n, size.as<int>());
     SMT_LAUNCH(ctx, spk_apply_kernel, nb, 256, 0, label.as<int>(), size.as<int>(), n, min_area, inv, disp);
     return SMT_OK;
 }

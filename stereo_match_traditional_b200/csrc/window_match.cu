@@ -414,6 +414,12 @@ __global__ void __launch_bounds__(256) asw_crosscheck_kernel(const float* __rest
     out[p] = fabsf((float)lv - rv) > 5.f ? 0 : (uint8_t)lv;
 }
 
+smt_status_t k_asw_crosscheck(smt_ctx* ctx, const float* dl, const float* dr, int H, int W, uint8_t* out) {
+    StageTimer t(ctx, ST_POST);
+    SMT_LAUNCH(ctx, asw_crosscheck_kernel, cdiv((long long)H * W, 256), 256, 0, dl, dr, H, W, out);
+    return SMT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- SAD cross-check (int maps)
 // CrossCheckDiaparity (SAD/Sad.h:184-221): rv = right[i][j - lv]; |lv - rv| > 5 -> invalid, occlusion if lv < rv else
 // mismatch; the marker written into the CV_32S map is (int)Invalid_Float, 2147483647 under g++.
@@ -670,10 +676,7 @@ smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, const floa
     const float* dr = ms.in(disp_right, n);
     uint8_t* dout = ms.out(out, n);
     SMT_TRY(ms.check());
-    {
-        StageTimer t(ctx, ST_POST);
-        SMT_LAUNCH(ctx, asw_crosscheck_kernel, cdiv((long long)n, 256), 256, 0, dl, dr, rows, cols, dout);
-    }
+    SMT_TRY(k_asw_crosscheck(ctx, dl, dr, rows, cols, dout));
     return ms.finish();
 }
 

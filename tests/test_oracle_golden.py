@@ -100,3 +100,21 @@ def test_port_fill_the_hole_matches_reference_golden(oracle_port):
     assert len(m) == 0 and (f == 65535).sum() > 0
     f, _ = oracle_port.fill_the_hole(d, 8, np.zeros((0, 2), np.int32), np.zeros((0, 2), np.int32))
     assert np.array_equal(f, d)
+
+
+def test_port_display_chain_matches_cv2_and_reference_golden(oracle_port):
+    """ASW display chain (ASWeight.cpp:66-78): the three OpenCV steps against cv2 4.13 outputs, FillImageNew against the
+    compiled reference (oracle/make_golden_display.py)."""
+    z = np.load(GOLDEN / "display.npz")
+    n = sum(1 for f in z.files if f.startswith("in"))
+    assert n >= 7
+    for k in range(n):
+        a = z[f"in{k}"]
+        assert np.array_equal(oracle_port.normalize_minmax_u8_from_u8(a), z[f"norm{k}"]), k
+        for tag, (nv, ms, md) in {"a": (0, 40, 2), "b": (0, 5, 0), "c": (7, 100, 10)}.items():
+            assert np.array_equal(oracle_port.filter_speckles_u8(a, nv, ms, md), z[f"speck{tag}{k}"]), (k, tag)
+        assert np.array_equal(oracle_port.median_blur_u8(a, 3), z[f"med3_{k}"]), k
+        assert np.array_equal(oracle_port.median_blur_u8(a, 5), z[f"med5_{k}"]), k
+        for pe in (0, 9):
+            if f"fill{pe}_{k}" in z.files:
+                assert np.array_equal(oracle_port.fill_image_new(a, pe)[0], z[f"fill{pe}_{k}"]), (k, pe)
