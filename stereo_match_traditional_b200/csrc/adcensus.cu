@@ -113,11 +113,11 @@ constexpr int COST_TJ = SMT_COST_TJ;
 // strings/values one row needs, then streams TJ*D cost cells with float4 stores (VEC=4) -- D innermost, coalesced.
 // PARTS: also write the AD and Hamming volumes (the int -> float conversions they need run at a quarter of the FP32 rate,
 // so the cost-only instantiation does not even compute them).
-template <int VEC, bool PARTS>
+template <int VEC, bool PARTS, int VIEW>
 __global__ void __launch_bounds__(256)
     adcensus_cost_kernel(const uint8_t* __restrict__ own_img, const uint8_t* __restrict__ oth_img,
                          const uint64_t* __restrict__ Cown, const uint64_t* __restrict__ Cext,
-                         const uint64_t* __restrict__ Mask, const float* __restrict__ lut, int H, int W, int D, int view,
+                         const uint64_t* __restrict__ Mask, const float* __restrict__ lut, int H, int W, int D,
                          int nmax, float* __restrict__ cost, float* __restrict__ ad, float* __restrict__ census) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_ext = reinterpret_cast<uint64_t*>(smem_raw);               // skew(nmax)+1
@@ -130,23 +130,23 @@ __global__ void __launch_bounds__(256)
     const int i = blockIdx.y;
     const int j0 = blockIdx.x * COST_TJ;
     const int jend = min(j0 + COST_TJ, W);
-    int xlo, xhi, ext_stride, ext_off;
-    if (view == 0) {  // x' = max(j-d, -3)
-        xlo = max(j0 - (D - 1), -3);
-        xhi = jend - 1;
+    // the strings / values of the other image at x' = max(j-d, -3) (view 0) or min(j+d, W+3) (view 1): staged for the whole
+    // unclamped range j-d (j+d) of the tile with the clamp applied here, so that the cell loop indexes without one
+    int xlo, ext_stride, ext_off;
+    if (VIEW == 0) {
+        xlo = j0 - (D - 1);
         ext_stride = W + 3;
         ext_off = 3;
-    } else {  // x' = min(j+d, W+3)
+    } else {
         xlo = j0;
-        xhi = min(jend - 1 + D - 1, W + 3);
         ext_stride = W + 4;
         ext_off = 0;
     }
-    const int n = xhi - xlo + 1;
+    const int n = (jend - j0) + D - 1;
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        int xv = xlo + q;
+        const int xv = VIEW == 0 ? max(xlo + q, -3) : min(xlo + q, W + 3);
         s_ext[skew(q)] = Cext[(size_t)i * ext_stride + xv + ext_off];
-        int xc = xv < 0 ? 0 : (xv > W - 1 ? W - 1 : xv);
+        const int xc = xv < 0 ? 0 : (xv > W - 1 ? W - 1 : xv);
         s_oth[q] = oth_img[(size_t)i * W + xc];
     }
     for (int q = threadIdx.x; q < jend - j0; q += blockDim.x) {
@@ -158,22 +158,30 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
 
     const int groups = (D + VEC - 1) / VEC;  // VEC==4 requires D%4==0
-    const int items = (jend - j0) * groups;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int pj = it / groups;
-        const int dg = it - pj * groups;
+    const int npj = jend - j0;
+    // item = (pixel pj, group dg of VEC disparities), items of a block walked 256 at a time: (pj, dg) advance by a fixed
+    // step with one carry instead of a division per item
+    int pj = threadIdx.x / groups, dg = threadIdx.x - pj * groups;
+    const int step_pj = 256 / groups, step_dg = 256 - step_pj * groups;
+    float* cost_row = cost + (size_t)i * W * D;
+    float* ad_row = PARTS && ad ? ad + (size_t)i * W * D : nullptr;
+    float* census_row = PARTS && census ? census + (size_t)i * W * D : nullptr;
+    for (; pj < npj; pj += step_pj, dg += step_dg) {
+        if (dg >= groups) {
+            dg -= groups;
+            if (++pj >= npj) break;
+        }
         const int j = j0 + pj;
         const uint64_t c0 = s_own[pj];
         const uint64_t m = s_msk[pj];
-        const int v0 = s_val[pj];
+        const unsigned v0 = s_val[pj];
         float oc[VEC], oa[VEC], oh[VEC];
+        const int q0 = VIEW == 0 ? pj + (D - 1) - dg * VEC : pj + dg * VEC;  // staged index of the group's first disparity
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const int d = dg * VEC + k;
-            const int xv = (view == 0) ? max(j - d, -3) : min(j + d, W + 3);
-            const int q = xv - xlo;
+            const int q = VIEW == 0 ? q0 - k : q0 + k;
             const uint64_t e = s_ext[skew(q)];
-            const int a = abs(v0 - (int)s_oth[q]);
+            const int a = (int)__usad(v0, (unsigned)s_oth[q], 0u);
             const int h = __popcll((c0 ^ e) & m);
             if (PARTS) {
                 oa[k] = (float)a;
@@ -181,15 +189,15 @@ __global__ void __launch_bounds__(256)
             }
             oc[k] = __fadd_rn(s_lut[a], s_lut[256 + h]);
         }
-        const size_t o = ((size_t)i * W + j) * D + (size_t)dg * VEC;
+        const int o = j * D + dg * VEC;  // inside one row: < 2^31 elements (checked by the launcher)
         if (VEC == 4) {
-            __stcs(reinterpret_cast<float4*>(cost + o), make_float4(oc[0], oc[1], oc[2], oc[3]));
-            if (PARTS && ad) __stcs(reinterpret_cast<float4*>(ad + o), make_float4(oa[0], oa[1], oa[2], oa[3]));
-            if (PARTS && census) __stcs(reinterpret_cast<float4*>(census + o), make_float4(oh[0], oh[1], oh[2], oh[3]));
+            __stcs(reinterpret_cast<float4*>(cost_row + o), make_float4(oc[0], oc[1], oc[2], oc[3]));
+            if (PARTS && ad) __stcs(reinterpret_cast<float4*>(ad_row + o), make_float4(oa[0], oa[1], oa[2], oa[3]));
+            if (PARTS && census) __stcs(reinterpret_cast<float4*>(census_row + o), make_float4(oh[0], oh[1], oh[2], oh[3]));
         } else {
-            cost[o] = oc[0];
-            if (PARTS && ad) ad[o] = oa[0];
-            if (PARTS && census) census[o] = oh[0];
+            cost_row[o] = oc[0];
+            if (PARTS && ad) ad_row[o] = oa[0];
+            if (PARTS && census) census_row[o] = oh[0];
         }
     }
 }
@@ -197,6 +205,7 @@ __global__ void __launch_bounds__(256)
 smt_status_t k_adcensus_cost(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, const CensusMaps& m, int H, int W, int D,
                              int view, float* cost, float* ad, float* census) {
     StageTimer t(ctx, ST_COST);
+    if ((long long)W * D >= 0x7fffffffLL) return smt_fail(ctx, SMT_ERR_UNSUPPORTED, "adcensus_cost: a row of %d x %d cells", W, D);
     const int nmax = D + COST_TJ + 3;
     size_t smem = sizeof(uint64_t) * (size_t)(nmax + (nmax >> 2) + 1 + 2 * COST_TJ) + 320 * sizeof(float) + nmax + COST_TJ;
     smem = (smem + 15) & ~size_t(15);
@@ -209,18 +218,24 @@ smt_status_t k_adcensus_cost(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, c
                       (!ad || (reinterpret_cast<uintptr_t>(ad) & 15) == 0) &&
                       (!census || (reinterpret_cast<uintptr_t>(census) & 15) == 0);
     const bool parts = ad != nullptr || census != nullptr;
-#define SMT_COST_LAUNCH(VEC_, PARTS_)                                                                                                \
+#define SMT_COST_LAUNCH2(VEC_, PARTS_, VIEW_)                                                                                                \
     do {                                                                                                                             \
         if (smem > 48 * 1024)                                                                                                        \
-            SMT_CUDA(ctx, cudaFuncSetAttribute(adcensus_cost_kernel<VEC_, PARTS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SMT_LAUNCH(ctx, (adcensus_cost_kernel<VEC_, PARTS_>), grid, 256, smem, own, oth, Cown, Cext, m.M, ctx->d_lut, H, W, D, view, nmax, \
+            SMT_CUDA(ctx, cudaFuncSetAttribute(adcensus_cost_kernel<VEC_, PARTS_, VIEW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SMT_LAUNCH(ctx, (adcensus_cost_kernel<VEC_, PARTS_, VIEW_>), grid, 256, smem, own, oth, Cown, Cext, m.M, ctx->d_lut, H, W, D, nmax, \
                    cost, ad, census);                                                                                                \
     } while (0)
-    if (vec4 && parts) SMT_COST_LAUNCH(4, true);
-    else if (vec4) SMT_COST_LAUNCH(4, false);
-    else if (parts) SMT_COST_LAUNCH(1, true);
-    else SMT_COST_LAUNCH(1, false);
-#undef SMT_COST_LAUNCH
+#define SMT_COST_VIEW(VEC_, PARTS_)                \
+    do {                                           \
+        if (view == 0) SMT_COST_LAUNCH2(VEC_, PARTS_, 0); \
+        else SMT_COST_LAUNCH2(VEC_, PARTS_, 1);    \
+    } while (0)
+    if (vec4 && parts) SMT_COST_VIEW(4, true);
+    else if (vec4) SMT_COST_VIEW(4, false);
+    else if (parts) SMT_COST_VIEW(1, true);
+    else SMT_COST_VIEW(1, false);
+#undef SMT_COST_VIEW
+#undef SMT_COST_LAUNCH2
     return SMT_OK;
 }
 
