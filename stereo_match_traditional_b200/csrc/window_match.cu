@@ -247,10 +247,21 @@ constexpr int ASW_TX = 4, ASW_TD = 32, ASW_Q = 4;  // columns per block, dispari
 // ASW_TX columns); thread = (column, disparity lane), each lane owns ASW_Q consecutive disparities.
 // cost = sum(wOwn*wOth*min(|a-b|,T)) / sum(wOwn*wOth) with w = colour[|p - centre|] * space[tap] (ASW.h:210-257), taps
 // accumulated in the reference's row-major order per cell; first-minimum WTA (:193-208).
-// The four windows of a lane in the other image are one pixel apart, so along a tap row they slide through a 4-deep
-// register window (one new byte per tap instead of four), and the own pixel, spatial weight and own-window weight of a
-// tap are read once for four cells.  The colour table is replicated per lane (index v*32 + lane): the lookups are
-// data-dependent and would otherwise collide in the banks.
+// The four windows of a lane in the other image are one pixel apart: along a tap row they read one sequence of pixels,
+// cell slot s at tap c taking element c + s (slot s = disparity d0 + s in the right view, d0 + 3 - s in the left view).
+// The sequence is loaded four elements at a time into a register window (one new byte per tap instead of four), and the
+// own pixel and the own-window weight of a tap are read once for four cells.  The colour table is replicated per lane
+// (index v*32 + lane): the lookups are data-dependent and would otherwise collide in the banks.
+// Per cell and tap: |q - centre| -> table address -> LDS, one multiply (the spatial weight of the other window is folded
+// into the own-window table: wOwn*space*space), |a - q| and min in float, one add, one fused multiply-add.
+// shared-memory load from a 32-bit shared address: lets the table lookup below be ONE multiply-add (index * 128 + lane base)
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+constexpr int ASW_PAD = ASW_Q - 1;  // columns of padding on both sides of a staged row of the other image: no clamps in the tap loop
+
 template <bool RIGHT>
 __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __restrict__ own_img, const uint8_t* __restrict__ oth_img,
                                                               int Hp, int Wp, int wins, int D, int T,
@@ -259,115 +270,124 @@ __global__ void __launch_bounds__(ASW_TX* ASW_TD) asw_kernel(const uint8_t* __re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = 2 * wins + 1, kk = k * k;
     const int Wo = Wp - 2 * wins;
-    const int own_w = ASW_TX + k - 1, oth_w = ASW_TX + k - 1 + D - 1;
-    float* s_space = reinterpret_cast<float*>(smem_raw);       // [kk]
-    float* s_colr = s_space + kk;                              // [256][32]
-    float* s_wown = s_colr + 256 * 32;                         // [ASW_TX][kk]
-    float* s_bestv = s_wown + ASW_TX * kk;                     // [ASW_TX][ASW_TD]
+    const int own_w = ASW_TX + k - 1, oth_w = ASW_TX + k - 1 + D - 1, oth_wp = oth_w + 2 * ASW_PAD + ASW_Q;
+    float* s_colr = reinterpret_cast<float*>(smem_raw);        // [256][32]
+    float* s_wown = s_colr + 256 * 32;                         // [ASW_TX][kk]: colour * space * space
+    float* s_ownf = s_wown + ASW_TX * kk;                      // [k][own_w] own pixels as float
+    float* s_bestv = s_ownf + k * own_w;                       // [ASW_TX][ASW_TD]
     int* s_bestd = reinterpret_cast<int*>(s_bestv + ASW_TX * ASW_TD);
-    uint8_t* s_own = reinterpret_cast<uint8_t*>(s_bestd + ASW_TX * ASW_TD);  // [k][own_w]
-    uint8_t* s_oth = s_own + (size_t)k * own_w;                             // [k][oth_w]
+    uint8_t* s_oth = reinterpret_cast<uint8_t*>(s_bestd + ASW_TX * ASW_TD);  // [k][oth_wp]
 
     const int io = blockIdx.y, jo0 = blockIdx.x * ASW_TX;
     const int tid = threadIdx.x, xl = tid / ASW_TD, dl = tid % ASW_TD, l32 = tid & 31;
-    const int oth_base = RIGHT ? jo0 : jo0 - (D - 1);  // padded column of s_oth[.][0]
-    for (int t = tid; t < kk; t += blockDim.x) s_space[t] = space[t];
+    const int oth_base = RIGHT ? jo0 : jo0 - (D - 1);  // padded-image column of staged column ASW_PAD
     for (int t = tid; t < 256 * 32; t += blockDim.x) s_colr[t] = color[t >> 5];
     for (int t = tid; t < k * own_w; t += blockDim.x) {
         const int r = t / own_w, c = t - r * own_w;
         const int x = jo0 + c;
-        s_own[t] = x < Wp ? own_img[(size_t)(io + r) * Wp + x] : 0;
+        s_ownf[t] = x < Wp ? (float)own_img[(size_t)(io + r) * Wp + x] : 0.f;
     }
-    for (int t = tid; t < k * oth_w; t += blockDim.x) {
-        const int r = t / oth_w, c = t - r * oth_w;
-        const int x = oth_base + c;
+    for (int t = tid; t < k * oth_wp; t += blockDim.x) {
+        const int r = t / oth_wp, c = t - r * oth_wp;
+        const int x = oth_base + c - ASW_PAD;
         s_oth[t] = (x >= 0 && x < Wp) ? oth_img[(size_t)(io + r) * Wp + x] : 0;
     }
     __syncthreads();
-    // weight table of each reference pixel: colour[|p - centre|] * space
+    // weight table of each reference pixel: colour[|p - centre|] * space, times the spatial weight of the other window
     for (int t = tid; t < ASW_TX * kk; t += blockDim.x) {
         const int x = t / kk, tap = t - x * kk;
         const int r = tap / k, c = tap - r * k;
-        const int centre = s_own[(size_t)wins * own_w + x + wins];
-        s_wown[t] = __fmul_rn(color[abs((int)s_own[(size_t)r * own_w + x + c] - centre)], s_space[tap]);
+        const float centre = s_ownf[(size_t)wins * own_w + x + wins];
+        const float sp = space[tap];
+        s_wown[t] = __fmul_rn(__fmul_rn(color[(int)fabsf(s_ownf[(size_t)r * own_w + x + c] - centre)], sp), sp);
     }
     __syncthreads();
 
     const int jo = jo0 + xl;
-    const float* colr = s_colr + l32;
+    const unsigned colr_addr = (unsigned)__cvta_generic_to_shared(s_colr + l32);
+    const float Tf = (float)T;
     float bestv = INFINITY;
     int bestd = 0x7fffffff;
     for (int d0 = dl * ASW_Q; d0 < D; d0 += ASW_TD * ASW_Q) {
         if (jo >= Wo) break;
-        // column (in s_oth) of the left edge of the window of disparity d0 + i: RIGHT: xl + d0 + i, else xl + D-1 - d0 - i
-        const int off0 = RIGHT ? xl + d0 : xl + (D - 1 - d0);
+        // staged column of element 0 of the lane's pixel sequence (left edge of slot 0's window)
+        const int B0 = ASW_PAD + (RIGHT ? xl + d0 : xl + (D - 1 - d0) - (ASW_Q - 1));
         int cb[ASW_Q];
 #pragma unroll
-        for (int i = 0; i < ASW_Q; ++i) {
-            const int o = min(max(RIGHT ? off0 + i : off0 - i, 0), oth_w - k);
-            cb[i] = s_oth[(size_t)wins * oth_w + o + wins];
-        }
+        for (int i = 0; i < ASW_Q; ++i) cb[i] = s_oth[(size_t)wins * oth_wp + B0 + i + wins];
         const float* wo = s_wown + xl * kk;
         float sw[ASW_Q], sv[ASW_Q];
 #pragma unroll
         for (int i = 0; i < ASW_Q; ++i) sw[i] = sv[i] = 0.f;
         for (int r = 0; r < k; ++r) {
-            const uint8_t* a = s_own + (size_t)r * own_w + xl;
-            const uint8_t* b = s_oth + (size_t)r * oth_w;
-            const float* sp = s_space + r * k;
+            const float* a = s_ownf + (size_t)r * own_w + xl;
+            const uint8_t* b = s_oth + (size_t)r * oth_wp + B0;
             const float* w0 = wo + r * k;
-            // pb[i] = other-image pixel of cell i at the current tap column
-            int pb[ASW_Q];
             // The reference accumulates both sums in double (ASW.h:212-255).  float32 accumulators are kept within the
             // 1e-5 bar by summing each tap row on its own and adding the row totals: <= (k-1) + (k-1) roundings on
             // positive terms instead of k*k - 1, i.e. a worst-case relative error of 48 * 2^-24 = 2.9e-6 for k = 25.
             float rw[ASW_Q], rv[ASW_Q];
 #pragma unroll
             for (int i = 0; i < ASW_Q; ++i) rw[i] = rv[i] = 0.f;
+            int q[2 * ASW_Q - 1];
+            float qf[2 * ASW_Q - 1];
 #pragma unroll
-            for (int i = 1; i < ASW_Q; ++i) {
-                // the three values that slide in from the previous columns (clamped: cells outside the range are discarded)
-                const int idx = RIGHT ? off0 + i - 1 : off0 - i;
-                pb[RIGHT ? i - 1 : i] = b[min(max(idx, 0), oth_w - 1)];
+            for (int i = 0; i < ASW_Q - 1; ++i) {
+                q[i] = b[i];
+                qf[i] = (float)q[i];
             }
-            for (int c = 0; c < k; ++c) {
-                const int pa = a[c];
-                const float spc = sp[c], w0c = w0[c];
-                if (RIGHT) {
-                    pb[ASW_Q - 1] = b[min(off0 + ASW_Q - 1 + c, oth_w - 1)];
-                } else {
-                    pb[0] = b[off0 + c];
-                }
+#define SMT_ASW_TAP(C, S0)                                                                  \
+    {                                                                                       \
+        const float pa = a[C], w = w0[C];                                                   \
+        _Pragma("unroll") for (int i = 0; i < ASW_Q; ++i) {                                 \
+            const float m2 = __fmul_rn(lds_f32(__usad((unsigned)q[(S0) + i], (unsigned)cb[i], 0u) * 128u + colr_addr), w); \
+            const float e = fminf(fabsf(pa - qf[(S0) + i]), Tf);                            \
+            rw[i] = __fadd_rn(rw[i], m2);                                                   \
+            rv[i] = __fmaf_rn(m2, e, rv[i]);                                                \
+        }                                                                                   \
+    }
+            int c = 0;
+            for (; c + ASW_Q <= k; c += ASW_Q) {
 #pragma unroll
                 for (int i = 0; i < ASW_Q; ++i) {
-                    const float m1 = __fmul_rn(colr[abs(pb[i] - cb[i]) * 32], spc);
-                    const float m2 = __fmul_rn(w0c, m1);
-                    const int e = min(abs(pa - pb[i]), T);
-                    rw[i] = __fadd_rn(rw[i], m2);
-                    rv[i] = __fadd_rn(rv[i], __fmul_rn(m2, (float)e));
+                    q[ASW_Q - 1 + i] = b[c + ASW_Q - 1 + i];
+                    qf[ASW_Q - 1 + i] = (float)q[ASW_Q - 1 + i];
                 }
-                if (RIGHT) {
 #pragma unroll
-                    for (int i = 0; i < ASW_Q - 1; ++i) pb[i] = pb[i + 1];
-                } else {
+                for (int s4 = 0; s4 < ASW_Q; ++s4) SMT_ASW_TAP(c + s4, s4)
 #pragma unroll
-                    for (int i = ASW_Q - 1; i > 0; --i) pb[i] = pb[i - 1];
+                for (int i = 0; i < ASW_Q - 1; ++i) {
+                    q[i] = q[ASW_Q + i];
+                    qf[i] = qf[ASW_Q + i];
                 }
             }
+            for (; c < k; ++c) {
+                q[ASW_Q - 1] = b[c + ASW_Q - 1];
+                qf[ASW_Q - 1] = (float)q[ASW_Q - 1];
+                SMT_ASW_TAP(c, 0)
+#pragma unroll
+                for (int i = 0; i < ASW_Q - 1; ++i) {
+                    q[i] = q[i + 1];
+                    qf[i] = qf[i + 1];
+                }
+            }
+#undef SMT_ASW_TAP
 #pragma unroll
             for (int i = 0; i < ASW_Q; ++i) {
                 sw[i] = __fadd_rn(sw[i], rw[i]);
                 sv[i] = __fadd_rn(sv[i], rv[i]);
             }
         }
+        // ascending d inside the thread: strict '<' keeps the first minimum
 #pragma unroll
-        for (int i = 0; i < ASW_Q; ++i) {
-            const int d = d0 + i;
+        for (int dd = 0; dd < ASW_Q; ++dd) {
+            const int i = RIGHT ? dd : ASW_Q - 1 - dd;  // slot of disparity d0 + dd
+            const int d = d0 + dd;
             const bool valid = d < D && (RIGHT ? (jo + d < Wo - wins - 1) : (jo - d >= 0));
             if (valid) {
                 const float cost = __fdiv_rn(sv[i], sw[i]);
                 if (costs) costs[((size_t)io * Wo + jo) * D + d] = cost;
-                if (cost < bestv) {  // ascending d inside the thread: strict '<' keeps the first minimum
+                if (cost < bestv) {
                     bestv = cost;
                     bestd = d;
                 }
@@ -628,8 +648,8 @@ smt_status_t smt_asw(smt_ctx* ctx, const uint8_t* left_padded, const uint8_t* ri
     DeviceGuard dev_guard(ctx->device);
     const int Ho = rows_padded - 2 * wins, Wo = cols_padded - 2 * wins;
     const size_t np = (size_t)rows_padded * cols_padded, no = (size_t)Ho * Wo;
-    const size_t smem = sizeof(float) * ((size_t)k * k + 256 * 32 + (size_t)ASW_TX * k * k + ASW_TX * ASW_TD) + sizeof(int) * ASW_TX * ASW_TD +
-                        (size_t)k * (ASW_TX + k - 1) + (size_t)k * (ASW_TX + k - 1 + D - 1);
+    const size_t smem = sizeof(float) * (256 * 32 + (size_t)ASW_TX * k * k + (size_t)k * (ASW_TX + k - 1) + ASW_TX * ASW_TD) +
+                        sizeof(int) * ASW_TX * ASW_TD + (size_t)k * (ASW_TX + k - 1 + D - 1 + 2 * ASW_PAD + ASW_Q);
     SMT_REQUIRE(ctx, smem <= 200 * 1024, SMT_ERR_UNSUPPORTED, "smt_asw: window / disparity range too large for the shared-memory tile");
     Marshal ms(ctx, space);
     const uint8_t* dl = ms.in(left_padded, np);
