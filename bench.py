@@ -297,13 +297,25 @@ def gpu_arm(args, H, W, D):
         for st2, _ in extra:
             stream.wait_stream(st2)
 
+    host_pool = None
+    if len(lanes) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        host_pool = ThreadPoolExecutor(max_workers=len(lanes))   # one host thread per context: the C call releases the GIL
+
+    def host_frame(eng_k, f, po):
+        fr = pin_frames[f]
+        return eng_k.pipeline(fr["bgr_left"].numpy(), fr["bgr_right"].numpy(), D, fr["gray_left"].numpy(), fr["gray_right"].numpy(),
+                              params=params, out=po.numpy())["disp"]
+
     def step_host():
-        outs = []
-        for f, po in zip(next_batch("host"), pin_out):
-            fr = pin_frames[f]
-            outs.append(eng.pipeline(fr["bgr_left"].numpy(), fr["bgr_right"].numpy(), D, fr["gray_left"].numpy(),
-                                     fr["gray_right"].numpy(), params=params, out=po.numpy())["disp"])
-        return outs
+        batch = list(zip(next_batch("host"), pin_out))
+        if host_pool is None:
+            return [host_frame(eng, f, po) for f, po in batch]
+        # the frames of a step alternate between the contexts, each driven by its own host thread, so that the copies of
+        # one frame overlap the kernels of another; every call still copies in, runs, copies out and synchronises
+        futs = [host_pool.submit(host_frame, lanes[k % len(lanes)][1], f, po) for k, (f, po) in enumerate(batch)]
+        return [fu.result() for fu in futs]
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -337,11 +349,15 @@ def gpu_arm(args, H, W, D):
     ms_e2e = timed(step_host, args.steps)
     fps_e2e = aggregate_fps(world, B, args.steps, ms_e2e)
 
-    # per-stage CUDA-event times for the roofline of the dominant kernel
+    # per-stage CUDA-event times for the roofline of the dominant kernel: frames one after the other on ONE context, so
+    # that a stage's events bracket its own kernels only (with --streams 2 the other stream's kernels would run in between)
     eng.stage_timing(True)
     nst = max(1, min(args.steps, 3))
-    for _ in range(nst):
-        step_device()
+    with torch.cuda.stream(stream):
+        for _ in range(nst):
+            for f in next_batch("dev"):
+                fr = dev_frames[f]
+                eng.pipeline(fr["bgr_left"], fr["bgr_right"], D, fr["gray_left"], fr["gray_right"], params=params)
     st = {k: v / (nst * B) for k, v in eng.read_stage_timing().items()}  # ms per frame
     eng.stage_timing(False)
     V = 4.0 * H * W * D
@@ -429,7 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=2)
-    ap.add_argument("--streams", type=int, default=1, help="contexts/streams the frames of a step are spread over")
+    ap.add_argument("--streams", type=int, default=2, help="contexts/streams (and host threads in the e2e leg) the frames of a step alternate between")
     ap.add_argument("--shape", default="1080x1920x256", help="HxWxD")
     ap.add_argument("--sum-mode", default="fast", choices=["fast", "reference_order"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
