@@ -37,14 +37,9 @@ void census_maps_carve(void* base, int H, int W, CensusMaps* m) {
 
 enum { CM_OWN = 0, CM_RIGHT_EXT = 1, CM_LEFT_EXT = 2, CM_MASK = 3 };
 
-// One thread per (row, column slot) of one map.
+// the 63-bit string of virtual column xv in row i, row-major taps, 1 where centre > tap (AD-Census.h:191-268)
 template <int mode>
-__global__ void __launch_bounds__(256) census_map_kernel(const uint8_t* __restrict__ img, int H, int W, int ncol,
-                                                         uint64_t* __restrict__ out) {
-    int xi = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
-    if (xi >= ncol) return;
-    const int xv = (mode == CM_RIGHT_EXT) ? xi - 3 : xi;  // virtual column
+__device__ __forceinline__ uint64_t census_bits(const uint8_t* __restrict__ img, int H, int W, int i, int xv) {
     int cc = xv < 0 ? 0 : (xv > W - 1 ? W - 1 : xv);
     const int centre = mode == CM_MASK ? 0 : img[(size_t)i * W + cc];
     uint64_t v = 0;
@@ -73,17 +68,35 @@ __global__ void __launch_bounds__(256) census_map_kernel(const uint8_t* __restri
             v |= bit ? 1ull : 0ull;
         }
     }
+    return v;
+}
+
+// One thread per (row, column slot) of one map.  The two "seen from the other image" maps differ from the image's own map
+// only where a tap leaves the row (columns within 3 of a border, and the slots beyond it): everywhere else they copy it.
+// The validity mask is all ones away from the borders.
+template <int mode>
+__global__ void __launch_bounds__(256) census_map_kernel(const uint8_t* __restrict__ img, int H, int W, int ncol,
+                                                         const uint64_t* __restrict__ own, uint64_t* __restrict__ out) {
+    int xi = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (xi >= ncol) return;
+    const int xv = (mode == CM_RIGHT_EXT) ? xi - 3 : xi;  // virtual column
+    const bool interior = xv >= 3 && xv <= W - 4;
+    uint64_t v;
+    if ((mode == CM_RIGHT_EXT || mode == CM_LEFT_EXT) && interior) v = own[(size_t)i * W + xv];
+    else if (mode == CM_MASK && interior && i >= 4 && i <= H - 5) v = 0x7fffffffffffffffull;
+    else v = census_bits<mode>(img, H, W, i, xv);
     out[(size_t)i * ncol + xi] = v;
 }
 
 smt_status_t k_census_maps(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, int H, int W, const CensusMaps& m) {
     StageTimer t(ctx, ST_CENSUS);
     dim3 blk(128);
-    SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, m.CL);
-    SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(W, 128), H), blk, 0, R, H, W, W, m.CR);
-    SMT_LAUNCH(ctx, census_map_kernel<CM_MASK>, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, m.M);
-    SMT_LAUNCH(ctx, census_map_kernel<CM_RIGHT_EXT>, dim3(cdiv(W + 3, 128), H), blk, 0, R, H, W, W + 3, m.CRx);
-    SMT_LAUNCH(ctx, census_map_kernel<CM_LEFT_EXT>, dim3(cdiv(W + 4, 128), H), blk, 0, L, H, W, W + 4, m.CLx);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, nullptr, m.CL);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(W, 128), H), blk, 0, R, H, W, W, nullptr, m.CR);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_MASK>, dim3(cdiv(W, 128), H), blk, 0, L, H, W, W, nullptr, m.M);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_RIGHT_EXT>, dim3(cdiv(W + 3, 128), H), blk, 0, R, H, W, W + 3, m.CR, m.CRx);
+    SMT_LAUNCH(ctx, census_map_kernel<CM_LEFT_EXT>, dim3(cdiv(W + 4, 128), H), blk, 0, L, H, W, W + 4, m.CL, m.CLx);
     return SMT_OK;
 }
 
@@ -242,55 +255,74 @@ smt_status_t k_adcensus_cost(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, c
 // ---------------------------------------------------------------------------------------------- WTA
 // One warp per pixel; lane l scans d = l, l+32, ... (coalesced 128 B per step) keeping its first minimum, then the
 // warp reduces (value, d) lexicographically, which is the reference's strict-'>' first minimum (AD-Census.h:359-372).
+constexpr int WTA_NP = 4;  // pixels per warp: their loads are issued together (the kernel is bound by load latency)
 template <bool VEC4>
 __global__ void __launch_bounds__(256) wta_first_min_kernel(const float* __restrict__ vol, size_t npix, int D,
                                                             float* __restrict__ disp) {
-    const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= npix) return;
+    const size_t pix0 = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WTA_NP;
+    if (pix0 >= npix) return;
     const int lane = threadIdx.x & 31;
-    const float* p = vol + pix * D;
-    float best = INFINITY;
-    int bd = 0x7fffffff;
+    float best[WTA_NP];
+    int bd[WTA_NP];
+#pragma unroll
+    for (int k = 0; k < WTA_NP; ++k) {
+        best[k] = INFINITY;
+        bd[k] = 0x7fffffff;
+    }
     if (VEC4) {
         // lane l owns d = 4l .. 4l+3 (+128, ...): 512 bytes per warp and request, ascending d inside the lane
         for (int d = lane * 4; d < D; d += 128) {
-            const float4 v = __ldcs(reinterpret_cast<const float4*>(p + d));
-            const float e[4] = {v.x, v.y, v.z, v.w};
+            float4 v[WTA_NP];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (e[k] < best || bd == 0x7fffffff) {
-                    best = e[k];
-                    bd = d + k;
-                }
+            for (int k = 0; k < WTA_NP; ++k)
+                v[k] = __ldcs(reinterpret_cast<const float4*>(vol + min(pix0 + k, npix - 1) * D + d));
+#pragma unroll
+            for (int k = 0; k < WTA_NP; ++k) {
+                const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (e[q] < best[k] || bd[k] == 0x7fffffff) {
+                        best[k] = e[q];
+                        bd[k] = d + q;
+                    }
+            }
         }
     } else {
         for (int d = lane; d < D; d += 32) {
-            float v = __ldcs(p + d);
-            if (v < best || bd == 0x7fffffff) {
-                best = v;
-                bd = d;
-            }
+            float v[WTA_NP];
+#pragma unroll
+            for (int k = 0; k < WTA_NP; ++k) v[k] = __ldcs(vol + min(pix0 + k, npix - 1) * D + d);
+#pragma unroll
+            for (int k = 0; k < WTA_NP; ++k)
+                if (v[k] < best[k] || bd[k] == 0x7fffffff) {
+                    best[k] = v[k];
+                    bd[k] = d;
+                }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int od = __shfl_xor_sync(0xffffffffu, bd, o);
-        if (od != 0x7fffffff && (bd == 0x7fffffff || ov < best || (ov == best && od < bd))) {
-            best = ov;
-            bd = od;
+    for (int k = 0; k < WTA_NP; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best[k], o);
+            int od = __shfl_xor_sync(0xffffffffu, bd[k], o);
+            if (od != 0x7fffffff && (bd[k] == 0x7fffffff || ov < best[k] || (ov == best[k] && od < bd[k]))) {
+                best[k] = ov;
+                bd[k] = od;
+            }
         }
+        if (lane == 0 && pix0 + k < npix) disp[pix0 + k] = (float)bd[k];
     }
-    if (lane == 0) disp[pix] = (float)bd;
 }
 
 smt_status_t k_wta(smt_ctx* ctx, const float* vol, int H, int W, int D, float* disp) {
     StageTimer t(ctx, ST_WTA);
     size_t npix = (size_t)H * W;
+    const unsigned nblk = (unsigned)cdiv((long long)npix, 8 * WTA_NP);
     if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0)
-        SMT_LAUNCH(ctx, wta_first_min_kernel<true>, cdiv((long long)npix, 8), 256, 0, vol, npix, D, disp);
+        SMT_LAUNCH(ctx, wta_first_min_kernel<true>, nblk, 256, 0, vol, npix, D, disp);
     else
-        SMT_LAUNCH(ctx, wta_first_min_kernel<false>, cdiv((long long)npix, 8), 256, 0, vol, npix, D, disp);
+        SMT_LAUNCH(ctx, wta_first_min_kernel<false>, nblk, 256, 0, vol, npix, D, disp);
     return SMT_OK;
 }
 
@@ -341,7 +373,7 @@ smt_status_t smt_census9x7_u64(smt_ctx* ctx, const float* img, int32_t rows, int
     SMT_TRY(k_f32_to_u8(ctx, di, npix, u8.as<uint8_t>()));
     {
         StageTimer t(ctx, ST_CENSUS);
-        SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(cols, 128), rows), 128, 0, u8.as<uint8_t>(), rows, cols, cols, dout);
+        SMT_LAUNCH(ctx, census_map_kernel<CM_OWN>, dim3(cdiv(cols, 128), rows), 128, 0, u8.as<uint8_t>(), rows, cols, cols, (const uint64_t*)nullptr, dout);
     }
     return ms.finish();
 }
