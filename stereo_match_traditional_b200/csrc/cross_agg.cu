@@ -289,20 +289,22 @@ smt_status_t k_aggregate_cross(smt_ctx* ctx, float* vol, float* tmp, const uint8
                                const uint16_t* sup1, int H, int W, int D, int iters, smt_sum_mode_t mode, float vmax, float** result,
                                float* wta_disp) {
     if (mode == SMT_SUM_FAST) return k_aggregate_cross_fast(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, vmax, result, wta_disp);
-    StageTimer t(ctx, ST_AGGREGATE);
     auto pass = [&](bool horiz, const float* src, float* dst, const uint16_t* s) -> smt_status_t {
         return k_agg_exact_pass(ctx, src, dst, arms8, s, H, W, D, horiz ? 1 : 0);
     };
     bool hfirst = true;
     float* cur = vol;
     float* oth = tmp;
-    for (int k = 0; k < iters; ++k) {
-        SMT_TRY(pass(hfirst, cur, oth, nullptr));
-        SMT_TRY(pass(!hfirst, oth, cur, hfirst ? sup0 : sup1));
-        hfirst = !hfirst;
+    {
+        StageTimer t(ctx, ST_AGGREGATE);
+        for (int k = 0; k < iters; ++k) {
+            SMT_TRY(pass(hfirst, cur, oth, nullptr));
+            SMT_TRY(pass(!hfirst, oth, cur, hfirst ? sup0 : sup1));
+            hfirst = !hfirst;
+        }
     }
     *result = cur;  // every iteration ends back in `vol`
-    if (wta_disp) SMT_TRY(k_wta(ctx, cur, H, W, D, wta_disp));
+    if (wta_disp) SMT_TRY(k_wta(ctx, cur, H, W, D, wta_disp));  // its own stage (ST_WTA)
     return SMT_OK;
 }
 

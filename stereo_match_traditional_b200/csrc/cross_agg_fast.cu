@@ -27,8 +27,8 @@ struct Pass {
 // measured twice and lost both times: the warp reduction per position costs the pass more than the separate streaming
 // WTA kernel (float pairs, round 1: 13.71 against 13.05 + 0.45 ms per frame; fixed point, round 2: 1.53 against
 // 0.79 + 0.46 ms for the one pass concerned).
-smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
-                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result, float* wta_disp) {
+static smt_status_t fast_sweeps(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0, const uint16_t* sup1,
+                                int H, int W, int D, int iters, float vmax, float** result) {
     StageTimer t(ctx, ST_AGGREGATE);
     // pass list (cross_aggregator.cpp:102-117): horizontal-first on even iterations; the second pass divides
     std::vector<Pass> passes;
@@ -85,6 +85,12 @@ smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const 
         oth = sw;
     }
     *result = cur;
-    if (wta_disp) SMT_TRY(k_wta(ctx, cur, H, W, D, wta_disp));
+    return SMT_OK;
+}
+
+smt_status_t k_aggregate_cross_fast(smt_ctx* ctx, float* vol, float* tmp, const uint8_t* arms8, const uint16_t* sup0,
+                                    const uint16_t* sup1, int H, int W, int D, int iters, float vmax, float** result, float* wta_disp) {
+    SMT_TRY(fast_sweeps(ctx, vol, tmp, arms8, sup0, sup1, H, W, D, iters, vmax, result));
+    if (wta_disp) SMT_TRY(k_wta(ctx, *result, H, W, D, wta_disp));  // its own stage (ST_WTA)
     return SMT_OK;
 }

@@ -216,7 +216,10 @@ __device__ __forceinline__ void fx1_chunk(FxAcc& acc, unsigned& bad, FxPre& pre,
                 float r = __uint2float_rn(eb[kk] - ea[kk]);
                 if (PRIMED) {
                     r = fx_div(r, dsc[kk].bq, dsc[kk].yq);
-                    bad |= fx_small(fx_quant(r, inv_q), vm1);  // the mean is the next iteration's tap
+                    // The taps of a dividing pass are not checked one by one (a raw sum of a redone line may be small):
+                    // the MEAN is.  The error of the window sum is at most (taps) x q/2 and the sum is count x mean with
+                    // count >= taps, so mean >= vmin bounds the relative error by 2^-20 like a per-tap check would.
+                    bad |= fx_small(fx_quant(r, inv_q), vm1);
                 } else {
                     r = __fmul_rn(r, q);
                 }
