@@ -152,7 +152,11 @@ def load() -> C.CDLL:
             "(or `make -C stereo_match_traditional_b200/csrc`). There is no CPU fallback.")
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:
+            if os.environ.get("SMT_B200_LIB"):   # an A/B build of an older revision may lack newer entry points
+                continue
+            raise ImportError(f"{LIB_PATH} does not export {name}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         fn.restype = res
         fn.argtypes = args
     _lib = lib

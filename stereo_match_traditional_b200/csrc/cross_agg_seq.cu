@@ -317,10 +317,9 @@ __global__ void __launch_bounds__(SEQ_WARPS * 32, SEQ_CTAS_PER_SM) agg_seq_kerne
     const int len = horiz ? W : H;
     const int st_lo0 = st_lo, st_hi0 = st_hi;
     // redo != nullptr: this launch is queued behind a fixed-point sweep (cross_agg_fx.cu) and only redoes the (line, chunk)
-    // tasks that sweep put on its list -- or every task once the sweep escalated.  The host does not know how many there
-    // are, so a redo launch is a small fixed grid whose warps stride over the list (a full grid of ~17 000 blocks that
-    // return at once costs more than the walks themselves); any other launch has one warp per task and leaves the loop
-    // after its first round.
+    // tasks that sweep put on its list -- or every task once the sweep escalated.  The grid has one warp per task of the
+    // sweep; listed (line, segment) items are spread over its warps with a stride (there can be more items than warps),
+    // warps beyond the list leave at once, and any other launch leaves the loop after its first round.
     // A listed line is cut into nseg segments walked by different warps: a handful of warps each walking a whole line
     // would leave the launch bound by the latency of one walk (~50 us at 1920 positions).  A segment starts its prefix
     // 48 positions early (outputs only read prefix entries up to 34 positions back) and stores its own positions only.
@@ -429,8 +428,10 @@ static smt_status_t launch_seq(smt_ctx* ctx, const float* in, float* out, const 
                                            (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
-    if (redo) nwarps = min(nwarps, (long long)ctx->sm_count * SEQ_CTAS_PER_SM * SEQ_WARPS);  // the warps stride over the list
+    const long long nwarps = (long long)(horiz ? H : W) * ((D + 31) / 32);
+    // One warp per task, also for redo launches: warps beyond the list leave at once.  (A small fixed grid whose warps stride
+    // over the list measured the same on listed sweeps and 11 % slower on escalated whole sweeps at 608 x 7680 x 512, where
+    // all warps then walk in lockstep; the task loop in the kernel is what is left of it.)
     // horizontal walk of a 256-disparity volume (the benchmark shape): the position step is a compile-time constant, so
     // the 32 loads and 32 stores of a chunk use immediate offsets from one base register (-27 % instructions, +1.3 %)
     if constexpr (NONNEG && !WTA) if (horiz && D == 256) {
