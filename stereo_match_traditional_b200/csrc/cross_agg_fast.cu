@@ -57,7 +57,9 @@ static smt_status_t fast_sweeps(smt_ctx* ctx, float* vol, float* tmp, const uint
     SMT_TRY(k_transpose_maps(ctx, arms8, sup0, H, W, armsT.as<uint8_t>(), sup0T.as<uint16_t>()));
     // a third volume for the float-pair redo of fused pairs: the listed lines' intermediate pass goes there, so that both
     // redo launches can cut their lines into segments (an in-place first pass has to walk whole lines, ~50 us each)
-    SMT_ALLOC(ctx, spare, fx && iters > 1 ? npix * (size_t)D * sizeof(float) : 0);
+    // (when the device cannot hold a third volume the first pass is redone in place: a line walk reads ahead of what it writes)
+    DevBuf spare(ctx, fx && iters > 1 ? npix * (size_t)D * sizeof(float) : 0);
+    if (!spare.ok()) cudaGetLastError();  // the failed allocation is not an error of this call
 
     for (size_t k = 0; k < passes.size();) {
         const int horiz = passes[k].horiz ? 1 : 0;
@@ -72,8 +74,9 @@ static smt_status_t fast_sweeps(smt_ctx* ctx, float* vol, float* tmp, const uint
         if (pair) {
             SMT_TRY(k_agg_fx_pair(ctx, cur, oth, amap, smap, H, W, D, horiz, tmaps, inv_q, q, state));
             // float-pair redo of the listed lines: A into the spare volume, then B from there into `oth`
-            SMT_TRY(k_agg_seq_pass(ctx, cur, spare.as<float>(), amap, smap, H, W, D, horiz, true, b_sum, tmaps, state));
-            SMT_TRY(k_agg_seq_pass(ctx, spare.as<float>(), oth, amap, nullptr, H, W, D, horiz, true, b_plain, tmaps, state));
+            float* mid = spare.ok() ? spare.as<float>() : cur;
+            SMT_TRY(k_agg_seq_pass(ctx, cur, mid, amap, smap, H, W, D, horiz, true, b_sum, tmaps, state));
+            SMT_TRY(k_agg_seq_pass(ctx, mid, oth, amap, nullptr, H, W, D, horiz, true, b_plain, tmaps, state));
             k += 2;
         } else {
             if (fx) SMT_TRY(k_agg_fx_pass(ctx, cur, oth, amap, smap, H, W, D, horiz, tmaps, inv_q, q, state));
