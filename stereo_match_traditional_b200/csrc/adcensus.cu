@@ -255,7 +255,10 @@ smt_status_t k_adcensus_cost(smt_ctx* ctx, const uint8_t* L, const uint8_t* R, c
 // ---------------------------------------------------------------------------------------------- WTA
 // One warp per pixel; lane l scans d = l, l+32, ... (coalesced 128 B per step) keeping its first minimum, then the
 // warp reduces (value, d) lexicographically, which is the reference's strict-'>' first minimum (AD-Census.h:359-372).
-constexpr int WTA_NP = 4;  // pixels per warp: their loads are issued together (the kernel is bound by load latency)
+#ifndef SMT_WTA_NP
+#define SMT_WTA_NP 4
+#endif
+constexpr int WTA_NP = SMT_WTA_NP;  // pixels per warp: their loads are issued together (the kernel is bound by load latency)
 template <bool VEC4>
 __global__ void __launch_bounds__(256) wta_first_min_kernel(const float* __restrict__ vol, size_t npix, int D,
                                                             float* __restrict__ disp) {
