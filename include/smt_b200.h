@@ -349,6 +349,11 @@ SMT_API smt_status_t smt_asw_crosscheck(smt_ctx* ctx, const float* disp_left, co
  *   smt_transform_to_show    TransformToShow (PostProcessing.h:137): (uchar)(int)disp, out-of-int-range floats -> 0
  *   smt_normalize_minmax_u8  normalize(src, dst, 0, 255, NORM_MINMAX) followed by convertTo(CV_8U)     main.cpp:106-111
  */
+/* cv::imwrite("*.png", 8-bit image) as the drivers use it for their results (AD-CensusV1/main.cpp:112-114,
+ * ASW/ASWeight.cpp:75-92): img uint8 [rows][cols][channels], channels 1 (grey) or 3 (BGR, written as RGB).  The pixel
+ * data is exact; the file is a valid PNG with stored deflate blocks, not byte-identical to OpenCV's libpng output. */
+SMT_API smt_status_t smt_write_png_u8(smt_ctx* ctx, const char* path, const uint8_t* img, int32_t rows, int32_t cols,
+                                      int32_t channels, smt_memspace_t space);
 SMT_API smt_status_t smt_bgr_to_gray(smt_ctx* ctx, const uint8_t* bgr, int32_t rows, int32_t cols, uint8_t* gray,
                                      smt_memspace_t space);
 SMT_API smt_status_t smt_replicate_pad(smt_ctx* ctx, const uint8_t* img, int32_t rows, int32_t cols, int32_t pad,

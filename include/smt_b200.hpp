@@ -409,6 +409,12 @@ inline void medianBlur(const uint8_t* src, uint8_t* dst, int rows, int cols, int
     }
     c.check(smt_median_blur_u8(c.get(), src, dst, rows, cols, ksize, SMT_HOST));
 }
+/// cv::imwrite(path, 8-bit image) for .png files (main.cpp:112-114, ASWeight.cpp:75-92)
+inline bool imwrite(const std::string& filename, const ImageView& img, Context& c = Context::Default()) {
+    const std::vector<uint8_t> d = img.dense();
+    c.check(smt_write_png_u8(c.get(), filename.c_str(), d.data(), img.rows, img.cols, img.channels, SMT_HOST));
+    return true;
+}
 
 }  // namespace smt
 #endif  // SMT_B200_HPP_

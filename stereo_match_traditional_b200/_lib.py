@@ -118,6 +118,7 @@ SIGNATURES = {
     "smt_median_blur_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "smt_fill_image_new": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i]),
     "smt_asw_display_chain": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "smt_write_png_u8": (_i, [_vp, C.c_char_p, _vp, _i, _i, _i, _i]),
     "smt_adcensus_default_params": (None, [C.POINTER(AdCensusParams), _i, _i, _i]),
     "smt_pipeline_adcensus_full": (_i, [_vp, C.POINTER(AdCensusParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
 }

@@ -613,6 +613,14 @@ class Engine:
         self._ck(self.lib.smt_asw_display_chain(self.h, pl, pr, H, W, p1, p2, p3, a.space))
         return o1, o2, o3
 
+    def write_png(self, path, img):
+        """imwrite(path, 8-bit image): grey [H][W] or BGR [H][W][3]."""
+        a = _Args(self, img)
+        H, W = img.shape[:2]
+        ch = 1 if img.ndim == 2 else int(img.shape[2])
+        pi = a.inp(img, np.uint8, (H, W) if ch == 1 else (H, W, ch))
+        self._ck(self.lib.smt_write_png_u8(self.h, str(path).encode(), pi, H, W, ch, a.space))
+
     # ------------------------------------------------------------------ full pipeline
     def default_params(self, H, W, D) -> AdCensusParams:
         p = AdCensusParams()

@@ -40,3 +40,48 @@ def test_driver_flow_raw_bgr_to_sad(engine, oracle):
     assert np.array_equal(gl, p["gray_left"]) and np.array_equal(gr, p["gray_right"])
     lp, rp = engine.replicate_pad(gl, 4), engine.replicate_pad(gr, 4)
     assert np.array_equal(engine.sad(lp, rp, 16, 3), oracle.sad(replicate_pad(p["gray_left"], 4), replicate_pad(p["gray_right"], 4), 16, 3))
+
+
+def _read_png(path):
+    """Minimal PNG reader (8-bit grey / RGB, filter type 0 rows only): no dependency on an image library."""
+    import struct
+    import zlib
+
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    at, idat, hdr = 8, b"", None
+    while at < len(b):
+        n, typ = struct.unpack(">I4s", b[at:at + 8])
+        data = b[at + 8:at + 8 + n]
+        assert struct.unpack(">I", b[at + 8 + n:at + 12 + n])[0] == zlib.crc32(typ + data) & 0xffffffff
+        if typ == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", data)
+        elif typ == b"IDAT":
+            idat += data
+        at += 12 + n
+    W, H, depth, ctype = hdr[:4]
+    ch = {0: 1, 2: 3}[ctype]
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(H, W * ch + 1)
+    assert depth == 8 and np.all(raw[:, 0] == 0)
+    return raw[:, 1:].reshape(H, W, ch) if ch == 3 else raw[:, 1:]
+
+
+def test_write_png(engine, tmp_path):
+    """imwrite of the drivers' 8-bit results (main.cpp:112-114): pixel-exact, readable by any PNG reader."""
+    rng = np.random.default_rng(5)
+    gray = rng.integers(0, 256, (375, 450), dtype=np.uint8)       # > 65535 bytes: several stored deflate blocks
+    bgr = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    engine.write_png(tmp_path / "g.png", gray)
+    engine.write_png(tmp_path / "c.png", bgr)
+    assert np.array_equal(_read_png(tmp_path / "g.png"), gray)
+    assert np.array_equal(_read_png(tmp_path / "c.png"), bgr[:, :, ::-1])   # stored as RGB
+    try:
+        import cv2
+    except ImportError:
+        return
+    assert np.array_equal(cv2.imread(str(tmp_path / "g.png"), cv2.IMREAD_UNCHANGED), gray)
+    assert np.array_equal(cv2.imread(str(tmp_path / "c.png"), cv2.IMREAD_UNCHANGED), bgr)
+    import torch
+
+    engine.write_png(tmp_path / "d.png", torch.as_tensor(gray, device="cuda"))   # device memspace
+    assert np.array_equal(_read_png(tmp_path / "d.png"), gray)
