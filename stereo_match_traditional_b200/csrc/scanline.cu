@@ -73,7 +73,10 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&r
 
 // VERT=false: line = row, walks x; VERT=true: line = column, walks y.  dir=+1 forward, -1 backward.
 template <int DPL, int VW, int PF, bool VERT>
-__global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__ cost, const float* __restrict__ gray, int H, int W,
+#ifndef SMT_SCAN_VMINB
+#define SMT_SCAN_VMINB 1  // minimum resident one-warp blocks per SM asked of the vertical instantiations (register cap)
+#endif
+__global__ void __launch_bounds__((VERT && SMT_SCAN_VMINB > 1) ? 32 : 64, VERT ? SMT_SCAN_VMINB : 1) scan_path_kernel(const float* __restrict__ cost, const float* __restrict__ gray, int H, int W,
                                                        int D, float p1, float p2init, int dir, float* __restrict__ path_out,
                                                        const float* acc_in, float* acc_out, float* __restrict__ disp, int zero) {
     __shared__ float s_p2[256];  // max(p1, p2Init / (d + 1)) for integer grey differences d
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(64) scan_path_kernel(const float* __restrict__
     }
 }
 
-template <int DPL, int VW, int PF>
+template <int DPL, int VW, int PF, int PFV = PF>
 static smt_status_t launch_paths(smt_ctx* ctx, const float* cost, const float* gray, int H, int W, int D, float p1, float p2,
                                  float* left, float* right, float* up, float* down, float* sum, float* disp, float* scratch) {
     const int WPB = 1;  // one scanline per block: 1080 / 1920 blocks spread evenly over the 148 SMs
@@ -256,10 +259,10 @@ static smt_status_t launch_paths(smt_ctx* ctx, const float* cost, const float* g
     SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, false>), cdiv(H, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, -1, right,
                (const float*)Lbuf, scratch, (float*)nullptr, 0);
     // pass 3: up; acc += up
-    SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, true>), cdiv(W, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, +1, up,
+    SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PFV, true>), cdiv(W, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, +1, up,
                (const float*)scratch, scratch, (float*)nullptr, 0);
     // pass 4: down; acc += down -> sum (optional) and WTA (optional)
-    SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PF, true>), cdiv(W, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, -1, down,
+    SMT_LAUNCH(ctx, (scan_path_kernel<DPL, VW, PFV, true>), cdiv(W, WPB), 32 * WPB, 0, cost, gray, H, W, D, p1, p2, -1, down,
                (const float*)scratch, sum, disp, 0);
     return SMT_OK;
 }
@@ -282,13 +285,20 @@ smt_status_t k_scanline(smt_ctx* ctx, const float* cost, const float* gray, int 
         }
     }
 #ifndef SMT_SCAN_PF8
-#define SMT_SCAN_PF8 6  // ring depth (steps) of the DPL = 8, float4 kernel, the 1080p x 256 case
+#define SMT_SCAN_PF8 4  // ring depth (steps) of the DPL = 8, float4 kernel, the 1080p x 256 case: horizontal passes
 #endif
 #define SMT_SCAN_CASE(DPL_, VW_, PF_) \
     if (dpl == DPL_ && vw == VW_)     \
         return launch_paths<DPL_, VW_, PF_>(ctx, cost, gray, H, W, D, fp1, fp2, left, right, up, down, sum, disp, scratch);
     SMT_SCAN_CASE(16, 4, 2)
-    SMT_SCAN_CASE(8, 4, SMT_SCAN_PF8)
+#ifndef SMT_SCAN_PFV8
+// The vertical passes have 1920 one-warp blocks: at depth 6 (216 registers, 9 warps per SM) they need two waves, at depth 2
+// (94 registers) one, and the lighter kernels share the SMs better with the other context's work.  Alone the stage
+// measures 4.19 (6, 6), 4.06 (6, 2), 4.13 (4, 2) ms; two contexts: 62.7, 62.9, 63.7 frames/s.
+#define SMT_SCAN_PFV8 2
+#endif
+    if (dpl == 8 && vw == 4)
+        return launch_paths<8, 4, SMT_SCAN_PF8, SMT_SCAN_PFV8>(ctx, cost, gray, H, W, D, fp1, fp2, left, right, up, down, sum, disp, scratch);
     SMT_SCAN_CASE(4, 4, 4)
     SMT_SCAN_CASE(16, 2, 2)
     SMT_SCAN_CASE(8, 2, 4)
